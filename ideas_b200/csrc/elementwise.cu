@@ -1,0 +1,178 @@
+// Library plumbing (error string, version) and the NHWC helpers of the modulation path:
+// channel scaling x*s[n,c] (stylegan2/model.py:239-240 applied to activations instead of
+// weights), the per-(sample,channel) dot products its backward needs, and the residual merge
+// (out+skip)/sqrt(2) of models.py:178,227.  All HBM-bound, 128-bit vectorised.
+#include "common.cuh"
+
+namespace ideas {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+__global__ void __launch_bounds__(256) scale_channels_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                             const float* __restrict__ s, int64_t pc4, int c4n,
+                                                             int64_t total4) {
+  // element v (float4 index) -> sample n = v / pc4, channel group = v % c4n
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total4; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = v / pc4;
+    const int cg = (int)(v % c4n);
+    const float4 a = ld_stream4(x + v * 4);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(s + n * c4n * 4) + cg);
+    st_stream4(out + v * 4, make_float4(a.x * m.x, a.y * m.y, a.z * m.z, a.w * m.w));
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_channels_scalar_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                                    const float* __restrict__ s, int64_t pc, int C,
+                                                                    int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = x[i] * __ldg(s + (i / pc) * C + (i % C));
+}
+
+// grid (slices, N); blockDim multiple of C/4 so each thread owns one channel group
+__global__ void __launch_bounds__(512) channel_dot_kernel(float* __restrict__ dot, float* __restrict__ out,
+                                                          const float* __restrict__ a, const float* __restrict__ b,
+                                                          const float* __restrict__ s, int64_t P, int c4n) {
+  extern __shared__ float4 red[];
+  const int n = blockIdx.y;
+  const int64_t pc4 = P * c4n;
+  const float* an = a + (int64_t)n * pc4 * 4;
+  const float* bn = b + (int64_t)n * pc4 * 4;
+  float* on = out ? out + (int64_t)n * pc4 * 4 : nullptr;
+  const int cg = threadIdx.x % c4n;
+  float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (s) m = __ldg(reinterpret_cast<const float4*>(s + (int64_t)n * c4n * 4) + cg);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < pc4; v += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = ld_stream4(an + v * 4);
+    const float4 y = ld_stream4(bn + v * 4);
+    acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y);
+    acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
+    if (on) st_stream4(on + v * 4, make_float4(y.x * m.x, y.y * m.y, y.z * m.z, y.w * m.w));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if ((int)threadIdx.x < c4n) {
+    float4 t = red[threadIdx.x];
+    for (int j = threadIdx.x + c4n; j < (int)blockDim.x; j += c4n) {
+      const float4 o = red[j];
+      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+    }
+    float* d = dot + ((int64_t)n * c4n + threadIdx.x) * 4;
+    atomicAdd(d + 0, t.x); atomicAdd(d + 1, t.y); atomicAdd(d + 2, t.z); atomicAdd(d + 3, t.w);
+  }
+}
+
+// generic fallback (any C): one CTA per (n, c)
+__global__ void __launch_bounds__(256) channel_dot_scalar_kernel(float* __restrict__ dot, float* __restrict__ out,
+                                                                 const float* __restrict__ a,
+                                                                 const float* __restrict__ b,
+                                                                 const float* __restrict__ s, int64_t P, int C) {
+  const int n = blockIdx.y, c = blockIdx.x;
+  const float m = s ? s[(int64_t)n * C + c] : 1.f;
+  float acc = 0.f;
+  for (int64_t p = threadIdx.x; p < P; p += blockDim.x) {
+    const int64_t i = ((int64_t)n * P + p) * C + c;
+    acc = fmaf(a[i], b[i], acc);
+    if (out) out[i] = b[i] * m;
+  }
+  __shared__ float sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(dot + (int64_t)n * C + c, sm[0]);
+}
+
+__global__ void __launch_bounds__(256) add_scale_kernel(float* __restrict__ out, const float* __restrict__ a,
+                                                        const float* __restrict__ b, float gain, int64_t n4) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = ld_stream4(a + v * 4), y = ld_stream4(b + v * 4);
+    st_stream4(out + v * 4, make_float4((x.x + y.x) * gain, (x.y + y.y) * gain, (x.z + y.z) * gain, (x.w + y.w) * gain));
+  }
+}
+__global__ void __launch_bounds__(256) add_scale_scalar_kernel(float* __restrict__ out, const float* __restrict__ a,
+                                                               const float* __restrict__ b, float gain, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (a[i] + b[i]) * gain;
+}
+
+static int blocks_for(int64_t items, int threads, int per_sm) {
+  int64_t b = ceil_div64(items, threads);
+  if (b > (int64_t)kNumSMs * per_sm) b = (int64_t)kNumSMs * per_sm;
+  return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace ideas
+
+using namespace ideas;
+
+extern "C" int ideas_abi_version(void) { return 1; }
+extern "C" const char* ideas_last_error(void) { return g_err; }
+
+extern "C" int ideas_device_cc(void) {
+  int dev = 0, major = 0, minor = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "device_cc");
+  return major * 10 + minor;
+}
+
+extern "C" int ideas_scale_channels(float* out, const float* x, const float* s, int N, int64_t P, int C, void* stream) {
+  IDEAS_REQUIRE(N >= 0 && P >= 0 && C >= 1, "scale_channels: bad shape");
+  const int64_t total = (int64_t)N * P * C;
+  if (total == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(out && x && s, "scale_channels: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C % 4 == 0 && aligned16(out) && aligned16(x) && aligned16(s)) {
+    scale_channels_kernel<<<blocks_for(total / 4, 256, 8), 256, 0, st>>>(out, x, s, P * (C / 4), C / 4, total / 4);
+  } else {
+    scale_channels_scalar_kernel<<<blocks_for(total, 256, 8), 256, 0, st>>>(out, x, s, P * C, C, total);
+  }
+  IDEAS_CHECK_LAUNCH("scale_channels");
+  return IDEAS_OK;
+}
+
+extern "C" int ideas_channel_dot(float* dot, float* out, const float* a, const float* b, const float* s, int N,
+                                 int64_t P, int C, void* stream) {
+  IDEAS_REQUIRE(N >= 0 && P >= 0 && C >= 1, "channel_dot: bad shape");
+  if ((int64_t)N * P == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(dot && a && b && (!out || s), "channel_dot: null pointer");
+  IDEAS_REQUIRE(N <= 65535, "channel_dot: batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int c4n = C / 4;
+  if (C % 4 == 0 && c4n <= 512 && aligned16(a) && aligned16(b) && (!out || aligned16(out)) && (!s || aligned16(s))) {
+    const int threads = c4n * (512 / c4n);
+    int slices = (int)ceil_div64(P * c4n, (int64_t)threads * 8);
+    const int cap = ceil_div(kNumSMs * 4, N);
+    if (slices > cap) slices = cap;
+    if (slices < 1) slices = 1;
+    channel_dot_kernel<<<dim3(slices, N), threads, threads * sizeof(float4), st>>>(dot, out, a, b, s, P, c4n);
+  } else {
+    channel_dot_scalar_kernel<<<dim3(C, N), 256, 0, st>>>(dot, out, a, b, s, P, C);
+  }
+  IDEAS_CHECK_LAUNCH("channel_dot");
+  return IDEAS_OK;
+}
+
+extern "C" int ideas_add_scale(float* out, const float* a, const float* b, float gain, int64_t n, void* stream) {
+  IDEAS_REQUIRE(n >= 0, "add_scale: negative size");
+  if (n == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(out && a && b, "add_scale: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n % 4 == 0 && aligned16(out) && aligned16(a) && aligned16(b))
+    add_scale_kernel<<<blocks_for(n / 4, 256, 8), 256, 0, st>>>(out, a, b, gain, n / 4);
+  else
+    add_scale_scalar_kernel<<<blocks_for(n, 256, 8), 256, 0, st>>>(out, a, b, gain, n);
+  IDEAS_CHECK_LAUNCH("add_scale");
+  return IDEAS_OK;
+}

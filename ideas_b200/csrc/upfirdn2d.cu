@@ -1,0 +1,187 @@
+// A4: upfirdn2d (zero-insert upsample -> pad/crop -> 2-D FIR -> decimate).
+// Replaces stylegan2/op/upfirdn2d.cpp:12-22 + upfirdn2d_kernel.cu:17-369 of the reference
+// (16x64 shared-memory tiles per 256-thread CTA, `volatile` smem, scalar loads, one (b,c)
+// plane per blockIdx.z).
+//
+// B200 design.  IDEAS only ever runs up = down = 1 with the 4x4 binomial kernel and
+// asymmetric zero padding: an HBM-bound stencil, 4 B read + 4 B written
+// per element.  Activations are NHWC, so the fast path assigns one thread to a group of
+// four channels (128-bit, fully coalesced across the warp) of one output column and lets
+// it slide down a strip of rows: every input row is loaded once per thread (4 taps along
+// x, neighbours hit L1), multiplied into the four kernel rows and accumulated into three
+// pending output rows held in registers -- no shared memory, no barriers.  An optional
+// epilogue applies bias + leaky ReLU (the Blur -> FusedLeakyReLU pair of an upsampling
+// StyledConv) so that tensor makes one HBM round trip instead of two.
+// Every other (up, down, kernel size, minor) combination -- used by the reference only in
+// Upsample/Downsample/ADA -- goes through a direct-form kernel with the same semantics.
+#include "common.cuh"
+
+namespace ideas {
+
+struct UpfirdnParams {
+  int major, in_h, in_w, minor, kh, kw;
+  int up_x, up_y, down_x, down_y, pad_x0, pad_y0;
+  int out_h, out_w;
+  float alpha, gain;
+};
+
+// ---------------------------------------------------------------------------------------
+// generic direct form, any parameters
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                                const float* __restrict__ kernel,
+                                                                const float* __restrict__ bias, UpfirdnParams p,
+                                                                int64_t total) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    int c = (int)(idx % p.minor);
+    int64_t t = idx / p.minor;
+    int ox = (int)(t % p.out_w);
+    t /= p.out_w;
+    int oy = (int)(t % p.out_h);
+    int m = (int)(t / p.out_h);
+    float v = 0.f;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      int uy = oy * p.down_y + ky - p.pad_y0;  // position in the zero-inserted signal
+      if (uy < 0 || uy % p.up_y) continue;
+      int iy = uy / p.up_y;
+      if (iy >= p.in_h) continue;
+      for (int kx = 0; kx < p.kw; ++kx) {
+        int ux = ox * p.down_x + kx - p.pad_x0;
+        if (ux < 0 || ux % p.up_x) continue;
+        int ix = ux / p.up_x;
+        if (ix >= p.in_w) continue;
+        // true convolution: tap (ky,kx) of the sliding window meets the flipped kernel
+        v += x[(((int64_t)m * p.in_h + iy) * p.in_w + ix) * p.minor + c] *
+             __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx));
+      }
+    }
+    if (bias) v = lrelu(v + __ldg(bias + c), p.alpha) * p.gain;
+    out[idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// fast path: up = down = 1, kernel <= 4x4, minor % 4 == 0 (NHWC)
+// ---------------------------------------------------------------------------------------
+struct Taps4 { float k[4][4]; };  // already flipped and zero-extended: k[ky][kx] meets in[oy+ky-pad][ox+kx-pad]
+
+__device__ __forceinline__ float4 fma4(const float4& a, float s, const float4& acc) {
+  return make_float4(fmaf(a.x, s, acc.x), fmaf(a.y, s, acc.y), fmaf(a.z, s, acc.z), fmaf(a.w, s, acc.w));
+}
+__device__ __forceinline__ float4 mul4(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+template <int ROWS, bool EPI>
+__global__ void __launch_bounds__(256) blur4_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                         const float* __restrict__ kernel,
+                                                         const float* __restrict__ bias, UpfirdnParams p) {
+  // taps: flipped (true convolution) and zero-extended to 4x4; 16 uniform loads per thread
+  Taps4 tp;
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx)
+      tp.k[ky][kx] = (ky < p.kh && kx < p.kw) ? __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)) : 0.f;
+  const int c4n = p.minor >> 2;
+  const int lin = blockIdx.x * blockDim.x + threadIdx.x;  // (ox, c4), c4 fastest
+  if (lin >= p.out_w * c4n) return;
+  const int ox = lin / c4n;
+  const int c = (lin - ox * c4n) << 2;
+  const int m = blockIdx.z;
+  const int oy0 = blockIdx.y * ROWS;
+  const int oy1 = min(oy0 + ROWS, p.out_h);
+  const int ix0 = ox - p.pad_x0;
+
+  const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
+  float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox) * p.minor + c;
+  const int64_t orow = (int64_t)p.out_w * p.minor;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI) b4 = *reinterpret_cast<const float4*>(bias + c);
+
+  bool colok[4];
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) colok[kx] = (ix0 + kx) >= 0 && (ix0 + kx) < p.in_w;
+
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
+  // input rows oy0-pad .. oy1-1-pad+3 ; output row (iy + pad - 3) completes at input row iy
+  const int iy_begin = oy0 - p.pad_y0;
+  const int iy_end = oy1 - 1 - p.pad_y0 + 3;
+  for (int iy = iy_begin; iy <= iy_end; ++iy) {
+    float4 r[4];
+    const bool rowok = iy >= 0 && iy < p.in_h;
+    const float* rp = xin + ((int64_t)iy * p.in_w + ix0) * p.minor;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      r[kx] = (rowok && colok[kx]) ? __ldg(reinterpret_cast<const float4*>(rp + (int64_t)kx * p.minor))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 h[4];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      float4 a = mul4(r[0], tp.k[ky][0]);
+      a = fma4(r[1], tp.k[ky][1], a);
+      a = fma4(r[2], tp.k[ky][2], a);
+      a = fma4(r[3], tp.k[ky][3], a);
+      h[ky] = a;
+    }
+    float4 done = make_float4(s2.x + h[3].x, s2.y + h[3].y, s2.z + h[3].z, s2.w + h[3].w);
+    s2 = make_float4(s1.x + h[2].x, s1.y + h[2].y, s1.z + h[2].z, s1.w + h[2].w);
+    s1 = make_float4(s0.x + h[1].x, s0.y + h[1].y, s0.z + h[1].z, s0.w + h[1].w);
+    s0 = h[0];
+    const int oy = iy + p.pad_y0 - 3;
+    if (oy >= oy0) {
+      if (EPI) {
+        done.x = lrelu(done.x + b4.x, p.alpha) * p.gain;
+        done.y = lrelu(done.y + b4.y, p.alpha) * p.gain;
+        done.z = lrelu(done.z + b4.z, p.alpha) * p.gain;
+        done.w = lrelu(done.w + b4.w, p.alpha) * p.gain;
+      }
+      st_stream4(o + (int64_t)oy * orow, done);
+    }
+  }
+}
+
+}  // namespace ideas
+
+using namespace ideas;
+
+extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, int major, int in_h, int in_w,
+                               int minor, int kernel_h, int kernel_w, int up_x, int up_y, int down_x, int down_y,
+                               int pad_x0, int pad_x1, int pad_y0, int pad_y1, const float* bias, float alpha,
+                               float gain, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IDEAS_REQUIRE(major >= 0 && in_h >= 0 && in_w >= 0 && minor >= 1, "upfirdn2d: bad input shape");
+  IDEAS_REQUIRE(kernel_h >= 1 && kernel_w >= 1, "upfirdn2d: empty FIR kernel");
+  IDEAS_REQUIRE(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d: up/down factors must be >= 1");
+  UpfirdnParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  // upfirdn2d_kernel.cu:236-239
+  p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kernel_h + down_y) / down_y;
+  p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kernel_w + down_x) / down_x;
+  p.alpha = alpha; p.gain = gain;
+  const bool empty = major == 0 || in_h == 0 || in_w == 0;
+  IDEAS_REQUIRE(empty || ((in_h * up_y + pad_y0 + pad_y1 - kernel_h) >= 0 && (in_w * up_x + pad_x0 + pad_x1 - kernel_w) >= 0),
+                "upfirdn2d: padding/cropping leaves no output (in %dx%d, kernel %dx%d)", in_h, in_w, kernel_h, kernel_w);
+  if (empty) return IDEAS_OK;
+  const int64_t total = (int64_t)major * p.out_h * p.out_w * minor;
+  if (total == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(out && x && kernel, "upfirdn2d: null pointer");
+
+  const bool fast = up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kernel_h <= 4 && kernel_w <= 4 &&
+                    minor % 4 == 0 && aligned16(out) && aligned16(x) && (!bias || aligned16(bias)) && major <= 65535;
+  if (fast) {
+    const int c4n = minor / 4;
+    constexpr int ROWS = 32;
+    dim3 grid(ceil_div(p.out_w * c4n, 256), ceil_div(p.out_h, ROWS), major);
+    if (bias) blur4_nhwc_kernel<ROWS, true><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
+    else blur4_nhwc_kernel<ROWS, false><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
+    IDEAS_CHECK_LAUNCH("upfirdn2d(fast)");
+    return IDEAS_OK;
+  }
+  int64_t blocks = ceil_div64(total, 256);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  upfirdn2d_generic_kernel<<<(int)blocks, 256, 0, st>>>(out, x, kernel, bias, p, total);
+  IDEAS_CHECK_LAUNCH("upfirdn2d(generic)");
+  return IDEAS_OK;
+}

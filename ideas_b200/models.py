@@ -1,0 +1,321 @@
+"""The seven IDEAS networks on the B200 layer library.
+
+Drop-in for the reference's models.py: ``init_model(name, args)`` (:468-513) and the classes
+it builds keep their names, constructor arguments, sub-module names/indices and therefore
+their state_dict keys (pinned by tests against tests/golden/contract.json),
+and parameters are drawn in the same order so a seeded construction reproduces the
+reference's initialisation bit for bit.
+
+What differs is underneath: ConvLayer runs a peephole pass over its children so that
+conv + FusedLeakyReLU execute as one kernel with a fused epilogue; residual merges are one
+kernel; all activations are NHWC; every convolution, blur and activation is hand-written
+CUDA behind the C ABI (no cuDNN, no per-sample weights).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .stylegan2.model import (Blur, EqualConv2d, EqualLinear, ScaledLeakyReLU,
+                              StyledConv_without_noise as StyledConv)
+from .stylegan2.op import FusedLeakyReLU
+from .stylegan2.op import conv2d as _ops
+from .stylegan2.op.conv2d import PackWeight
+from .stylegan2.op.elementwise import add_scale
+
+_INV_SQRT2 = 1.0 / math.sqrt(2.0)
+
+
+class EqualConvTranspose2d(nn.Module):
+    """Equalised-lr transposed convolution; weight is (in, out, k, k) as in models.py:17-19."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(in_channel, out_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride = stride
+        self.padding = padding
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+
+    def forward(self, input):
+        cin, cout, k, _ = self.weight.shape
+        # (in, out, k, k) is the OIHW weight of the stride-s conv whose adjoint this layer is
+        wp = PackWeight.apply(self.weight, False, self.scale)
+        out = _ops.conv_transpose2d(input, wp, C_out=cout, kh=k, kw=k, stride=self.stride, pad=self.padding)
+        if self.bias is not None:
+            out = out + self.bias.view(1, -1, 1, 1)
+        return out
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.weight.shape[0]}, {self.weight.shape[1]},"
+                f" {self.weight.shape[2]}, stride={self.stride}, padding={self.padding})")
+
+
+def _blur_pads(blur_kernel, kernel_size, up):
+    """Blur padding around a stride-2 (transposed) conv, reference models.py:68-74,90-95."""
+    factor = 2
+    if up:
+        p = (len(blur_kernel) - factor) - (kernel_size - 1)
+        return ((p + 1) // 2 + factor - 1, p // 2 + 1)
+    p = (len(blur_kernel) - factor) + (kernel_size - 1)
+    return ((p + 1) // 2, p // 2)
+
+
+class ConvLayer(nn.Sequential):
+    """[Blur] conv | convT Blur | [ReflectionPad] conv, then FusedLeakyReLU / ScaledLeakyReLU / Tanh.
+    Child order and indices follow models.py:49-134 exactly (they are the state_dict keys)."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, upsample=False, downsample=False,
+                 blur_kernel=(1, 3, 3, 1), bias=True, activate=True, padding="zero", tanh=False):
+        stages = []
+        conv_bias = bias and not activate
+        if downsample:
+            stages.append(Blur(blur_kernel, pad=_blur_pads(blur_kernel, kernel_size, up=False)))
+        if upsample:
+            stages.append(EqualConvTranspose2d(in_channel, out_channel, kernel_size, padding=0, stride=2,
+                                               bias=conv_bias))
+            stages.append(Blur(blur_kernel, pad=_blur_pads(blur_kernel, kernel_size, up=True)))
+            conv_pad = 0
+        else:
+            conv_pad = 0
+            if not downsample:
+                half = (kernel_size - 1) // 2
+                if padding == "zero":
+                    conv_pad = half
+                elif padding == "reflect":
+                    if half > 0:
+                        stages.append(nn.ReflectionPad2d(half))
+                elif padding != "valid":
+                    raise ValueError('Padding should be "zero", "reflect", or "valid"')
+            stages.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=conv_pad,
+                                      stride=2 if downsample else 1, bias=conv_bias))
+        if activate:
+            if tanh:
+                stages.append(nn.Tanh())
+            elif bias:
+                stages.append(FusedLeakyReLU(out_channel))
+            else:
+                stages.append(ScaledLeakyReLU(0.2))
+        super().__init__(*stages)
+        self.padding = conv_pad
+
+    def forward(self, input):
+        mods = list(self)
+        i, out = 0, input
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(m, EqualConv2d) and isinstance(nxt, FusedLeakyReLU):
+                out = m(out, activation=nxt)          # one kernel: conv + bias + leaky ReLU
+                i += 2
+            else:
+                out = m(out)
+                i += 1
+        return out
+
+
+class StyledResBlock(nn.Module):
+    def __init__(self, in_channel, out_channel, style_dim, upsample, blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        self.conv1 = StyledConv(in_channel, out_channel, 3, style_dim, upsample=upsample, blur_kernel=blur_kernel)
+        self.conv2 = StyledConv(out_channel, out_channel, 3, style_dim)
+        self.skip = None
+        if upsample or in_channel != out_channel:
+            self.skip = ConvLayer(in_channel, out_channel, 1, upsample=upsample, blur_kernel=blur_kernel,
+                                  bias=False, activate=False)
+
+    def forward(self, input, style, noise=None):
+        out = self.conv2(self.conv1(input, style, noise), style, noise)
+        skip = input if self.skip is None else self.skip(input)
+        return add_scale(out, skip, _INV_SQRT2)
+
+
+class ResBlock(nn.Module):
+    def __init__(self, in_channel, out_channel, downsample, padding="zero", blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, out_channel, 3, padding=padding)
+        self.conv2 = ConvLayer(out_channel, out_channel, 3, downsample=downsample, padding=padding,
+                               blur_kernel=blur_kernel)
+        self.skip = None
+        if downsample or in_channel != out_channel:
+            self.skip = ConvLayer(in_channel, out_channel, 1, downsample=downsample, blur_kernel=blur_kernel,
+                                  bias=False, activate=False)
+
+    def forward(self, input):
+        out = self.conv2(self.conv1(input))
+        skip = input if self.skip is None else self.skip(input)
+        return add_scale(out, skip, _INV_SQRT2)
+
+
+class DisentanglementEncoder(nn.Module):
+    """image -> (structure code (B, structure_channel, H/16, W/16), texture vector (B, texture_channel))."""
+
+    def __init__(self, channel, structure_channel=8, texture_channel=2048, blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        widths = [channel * 2 ** i for i in range(5)]
+        stem = [ConvLayer(3, widths[0], 1)]
+        stem += [ResBlock(a, b, downsample=True, padding="reflect", blur_kernel=blur_kernel)
+                 for a, b in zip(widths[:-1], widths[1:])]
+        self.stem = nn.Sequential(*stem)
+        top = widths[-1]
+        self.structure = nn.Sequential(ConvLayer(top, top, 1, blur_kernel=blur_kernel),
+                                       ConvLayer(top, structure_channel, 1, blur_kernel=blur_kernel))
+        self.texture = nn.Sequential(
+            ConvLayer(top, top * 2, 3, downsample=True, padding="valid", blur_kernel=blur_kernel),
+            ConvLayer(top * 2, top * 4, 3, downsample=True, padding="valid", blur_kernel=blur_kernel),
+            nn.AdaptiveAvgPool2d(1),
+            ConvLayer(top * 4, texture_channel, 1, tanh=True, blur_kernel=blur_kernel))
+
+    def forward(self, input):
+        feat = self.stem(input)
+        return self.structure(feat), torch.flatten(self.texture(feat), 1)
+
+
+class Generator(nn.Module):
+    """(structure code, texture vector) -> image through 8 styled residual blocks (4 at 1/16
+    resolution, 4 upsampling) and a 1x1 to-RGB conv."""
+
+    CH_MULT = (4, 8, 12, 16, 16, 16, 8, 4)
+    UPSAMPLE = (False, False, False, False, True, True, True, True)
+
+    def __init__(self, channel, structure_channel=8, texture_channel=2048, blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        width = structure_channel
+        for mult, up in zip(self.CH_MULT, self.UPSAMPLE):
+            self.layers.append(StyledResBlock(width, channel * mult, texture_channel, up, blur_kernel))
+            width = channel * mult
+        self.to_rgb = ConvLayer(width, 3, 1, activate=False)
+
+    def forward(self, structure, texture, noises=None):
+        noises = noises if noises is not None else [None] * len(self.layers)
+        out = structure
+        for block, noise in zip(self.layers, noises):
+            out = block(out, texture, noise)
+        return self.to_rgb(out)
+
+
+def _same_res_stack(c_in, widths, c_out, blur_kernel):
+    layers = [ConvLayer(c_in, widths[0], 1, blur_kernel=blur_kernel)]
+    layers += [ResBlock(a, b, downsample=False, padding="reflect", blur_kernel=blur_kernel)
+               for a, b in zip(widths[:-1], widths[1:])]
+    layers.append(ConvLayer(widths[-1], c_out, 1, blur_kernel=blur_kernel))
+    return nn.Sequential(*layers)
+
+
+class StructureGenerator(nn.Module):
+    """secret tensor Z (B, N, h, w) -> structure code (B, structure_channel, h, w)."""
+
+    def __init__(self, channel, N=1, structure_channel=8, blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        self.structure = _same_res_stack(N, (channel, channel * 2, channel * 4, channel * 2), structure_channel,
+                                         blur_kernel)
+
+    def forward(self, noise):
+        return self.structure(noise)
+
+
+class ImageLevelDiscriminator(nn.Module):
+    def __init__(self, size, channel_multiplier=1, blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        m = channel_multiplier
+        channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * m, 128: 128 * m, 256: 64 * m, 512: 32 * m,
+                    1024: 16 * m}
+        width = channels[size]
+        convs = [ConvLayer(3, width, 1, blur_kernel=blur_kernel)]
+        for level in range(int(math.log(size, 2)), 2, -1):
+            nxt = channels[2 ** (level - 1)]
+            convs.append(ResBlock(width, nxt, downsample=True, blur_kernel=blur_kernel))
+            width = nxt
+        self.convs = nn.Sequential(*convs)
+        self.final_conv = ConvLayer(width, channels[4], 3, blur_kernel=blur_kernel)
+        self.final_linear = nn.Sequential(EqualLinear(channels[4] * 4 * 4, channels[4], activation="fused_lrelu"),
+                                          EqualLinear(channels[4], 1))
+
+    def forward(self, input):
+        out = self.final_conv(self.convs(input))
+        # flatten in the logical (C, H, W) order the linear layer's weights expect
+        return self.final_linear(out.reshape(out.shape[0], -1))
+
+
+class CooccurenceDiscriminator(nn.Module):
+    CH_MULT = (2, 4, 8, 12, 12, 24)
+    DOWNSAMPLE = (True, True, True, True, True, False)
+
+    def __init__(self, channel, size=256):
+        super().__init__()
+        encoder = [ConvLayer(3, channel, 1)]
+        width = channel
+        for mult, down in zip(self.CH_MULT, self.DOWNSAMPLE):
+            encoder.append(ResBlock(width, channel * mult, down))
+            width = channel * mult
+        k_size, feat_size = (3, 2 * 2) if size > 511 else (2, 1 * 1)
+        encoder.append(ConvLayer(width, channel * 12, k_size, padding="valid"))
+        self.encoder = nn.Sequential(*encoder)
+        self.linear = nn.Sequential(
+            EqualLinear(channel * 12 * 2 * feat_size, channel * 32, activation="fused_lrelu"),
+            EqualLinear(channel * 32, channel * 32, activation="fused_lrelu"),
+            EqualLinear(channel * 32, channel * 16, activation="fused_lrelu"),
+            EqualLinear(channel * 16, 1))
+
+    def forward(self, input, reference=None, ref_batch=None, ref_input=None):
+        feat = self.encoder(input)
+        if ref_input is None:
+            ref = self.encoder(reference)
+            _, c, h, w = ref.shape
+            ref_input = ref.reshape(-1, ref_batch, c, h, w).mean(1)
+        out = torch.flatten(torch.cat((feat, ref_input), 1), 1)
+        return self.linear(out), ref_input
+
+
+class DistributionDiscriminator(nn.Module):
+    def __init__(self, texture_channel=2048):
+        super().__init__()
+        t = texture_channel
+        dims = (t, t // 4, t // 16, t // 64, 1)
+        self.model = nn.Sequential(*[EqualLinear(a, b, activation="fused_lrelu") for a, b in zip(dims[:-1], dims[1:])])
+
+    def forward(self, input):
+        return self.model(input)
+
+
+class TensorExtractor(nn.Module):
+    """recovered structure code -> secret tensor estimate (B, N, h, w)."""
+
+    def __init__(self, channel, N=1, structure_channel=8, blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        self.extract = _same_res_stack(structure_channel, (channel * 2, channel * 4, channel * 2, channel), N,
+                                       blur_kernel)
+
+    def forward(self, input):
+        return self.extract(input)
+
+
+_FACTORIES = {
+    "DisentanglementEncoder": lambda a: DisentanglementEncoder(channel=a.channel, structure_channel=a.structure_channel,
+                                                               texture_channel=a.texture_channel,
+                                                               blur_kernel=a.blur_kernel),
+    "Generator": lambda a: Generator(channel=a.channel, structure_channel=a.structure_channel,
+                                     texture_channel=a.texture_channel, blur_kernel=a.blur_kernel),
+    "StructureGenerator": lambda a: StructureGenerator(channel=a.channel, N=a.N, structure_channel=a.structure_channel,
+                                                       blur_kernel=a.blur_kernel),
+    "ImageLevelDiscriminator": lambda a: ImageLevelDiscriminator(size=a.image_size,
+                                                                 channel_multiplier=a.channel_multiplier,
+                                                                 blur_kernel=a.blur_kernel),
+    "CooccurenceDiscriminator": lambda a: CooccurenceDiscriminator(channel=a.channel, size=a.image_size),
+    "DistributionDiscriminator": lambda a: DistributionDiscriminator(texture_channel=a.texture_channel),
+    "TensorExtractor": lambda a: TensorExtractor(channel=a.channel, N=a.N, structure_channel=a.structure_channel,
+                                                 blur_kernel=a.blur_kernel),
+}
+
+
+def init_model(model, args):
+    """Same contract as the reference's ``init_model`` (models.py:468-513): build one network by
+    name from the fields of ``args`` (train.py:341-370)."""
+    try:
+        factory = _FACTORIES[model]
+    except KeyError:
+        raise NotImplementedError(model) from None
+    return factory(args)

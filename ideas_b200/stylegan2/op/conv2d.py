@@ -1,0 +1,360 @@
+"""Convolution family on the B200 C ABI (new native unit).
+
+The reference computes every convolution with cuDNN through ``F.conv2d`` /
+``F.conv_transpose2d`` (stylegan2/model.py:115,258,267,273; models.py:32) and, for the
+modulated convolution, on per-sample weights materialised as a (B*Cout, Cin, k, k) tensor
+(stylegan2/model.py:240-275).  Here the three GEMMs of a convolution are explicit autograd
+Functions over NHWC activations and *packed* weights ``wp[tap][K][C]``:
+
+    ConvFwd(x, wp)    y  = conv(x, w)                      (+ bias, leaky ReLU epilogue)
+    ConvDgrad(dy, wp) dx = conv_transpose(dy, w)           (also the forward of a transposed conv)
+    ConvWgrad(x, dy)  dwp
+
+Each one's backward is written with the other two, so gradients of any order exist -- the
+R1 penalty (reference utils.py:112-118) needs second order through the discriminators.
+``ModConv`` / ``ModConvUp`` implement ModulatedConv2d + FusedLeakyReLU (and the upsampling
+variant with its Blur) as  act(d * conv(s * x) + b)  -- algebraically identical to the
+reference's weight modulation/demodulation, never building per-sample weights.
+
+Nothing here saves a leaf parameter for backward: only packed copies are saved, so the
+reference's second ``backward()`` over a retained graph after ``optimizer.step()``
+(train.py:209-216) keeps working.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ... import _lib
+from ..._tensor import empty_nhwc, nhwc, ptr, require_cuda, stream_ptr
+from .fused_act import FusedLeakyReLUFunctionBackward
+from .upfirdn2d import UpFirDn2dBackward, _grad_pad, _run as _upfirdn_run
+
+DEFAULT_IMPL = _lib.IMPL_AUTO          # tests flip this to compare SIMT and tcgen05 paths
+
+
+def set_default_impl(impl: int) -> int:
+    global DEFAULT_IMPL
+    old, DEFAULT_IMPL = DEFAULT_IMPL, impl
+    return old
+
+
+class Geom(NamedTuple):
+    """Forward-convolution geometry: x (N,C,H,W) -> y (N,K,OH,OW)."""
+    N: int
+    H: int
+    W: int
+    C: int
+    K: int
+    kh: int
+    kw: int
+    stride: int
+    pad: int
+    OH: int
+    OW: int
+
+    @staticmethod
+    def forward(x_shape, K, kh, kw, stride, pad) -> "Geom":
+        n, c, h, w = x_shape
+        return Geom(n, h, w, c, K, kh, kw, stride, pad, (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1)
+
+    @staticmethod
+    def transposed(x_shape, C_out, kh, kw, stride, pad) -> "Geom":
+        """Geometry whose *dgrad* is conv_transpose2d(x): x plays dy (N,K,OH,OW)."""
+        n, k, oh, ow = x_shape
+        return Geom(n, (oh - 1) * stride + kh - 2 * pad, (ow - 1) * stride + kw - 2 * pad, C_out, k, kh, kw, stride, pad, oh, ow)
+
+
+# --------------------------------------------------------------------------- raw launches
+def _fwd(x, wp, g: Geom, in_scale=None, out_scale=None, bias=None, act=_lib.ACT_NONE, alpha=0.2, gain=1.0, impl=None):
+    y = empty_nhwc(g.N, g.K, g.OH, g.OW, x)
+    _lib.call("ideas_conv2d_forward", ptr(y), ptr(x), ptr(wp), ptr(in_scale), ptr(out_scale), ptr(bias),
+              g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, act, float(alpha), float(gain),
+              DEFAULT_IMPL if impl is None else impl, stream_ptr(x))
+    return y
+
+
+def _dgrad(dy, wp, g: Geom, in_scale=None, out_scale=None, impl=None):
+    """dx (N,C,H,W) = in_scale * conv_transpose(out_scale * dy, w)."""
+    wpt = torch.empty_like(wp)
+    _lib.call("ideas_repack_dgrad", ptr(wpt), ptr(wp), g.K, g.C, g.kh * g.kw, stream_ptr(dy))
+    dx = empty_nhwc(g.N, g.C, g.H, g.W, dy)
+    _lib.call("ideas_conv2d_dgrad", ptr(dx), ptr(dy), ptr(wpt), ptr(in_scale), ptr(out_scale), ptr(None),
+              g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, g.OH, g.OW, _lib.ACT_NONE, 0.2, 1.0,
+              DEFAULT_IMPL if impl is None else impl, stream_ptr(dy))
+    return dx
+
+
+def _wgrad(x, dy, g: Geom, in_scale=None, out_scale=None, impl=None):
+    dwp = torch.zeros((g.kh * g.kw, g.K, g.C), device=x.device, dtype=x.dtype)
+    _lib.call("ideas_conv2d_wgrad", ptr(dwp), ptr(x), ptr(dy), ptr(in_scale), ptr(out_scale),
+              g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, g.OH, g.OW,
+              DEFAULT_IMPL if impl is None else impl, stream_ptr(x))
+    return dwp
+
+
+def _check(x, shape, what):
+    if tuple(x.shape) != tuple(shape):
+        raise RuntimeError(f"{what}: expected shape {tuple(shape)}, got {tuple(x.shape)}")
+
+
+# --------------------------------------------------------------------------- weight packing
+class PackWeight(Function):
+    """(O, I, kh, kw) parameter * scale -> packed (taps, O, I)  [transpose=False]
+                                        or (taps, I, O)        [transpose=True]."""
+
+    @staticmethod
+    def forward(ctx, w, transpose, scale):
+        require_cuda(w)
+        w = w.contiguous()
+        o, i, kh, kw = w.shape
+        ctx.cfg = (o, i, kh, kw, transpose, scale)
+        dst = torch.empty((kh * kw, i, o) if transpose else (kh * kw, o, i), device=w.device, dtype=w.dtype)
+        _lib.call("ideas_pack_weight", ptr(dst), ptr(w), o, i, kh, kw, int(transpose), 0, float(scale), stream_ptr(w))
+        return dst
+
+    @staticmethod
+    def backward(ctx, g):
+        o, i, kh, kw, transpose, scale = ctx.cfg
+        return UnpackWeight.apply(g, o, i, kh, kw, transpose, scale), None, None
+
+
+class UnpackWeight(Function):
+    @staticmethod
+    def forward(ctx, g, o, i, kh, kw, transpose, scale):
+        g = g.contiguous()
+        ctx.cfg = (transpose, scale)
+        dst = torch.empty((o, i, kh, kw), device=g.device, dtype=g.dtype)
+        _lib.call("ideas_unpack_weight_grad", ptr(dst), ptr(g), o, i, kh, kw, int(transpose), float(scale), 0,
+                  stream_ptr(g))
+        return dst
+
+    @staticmethod
+    def backward(ctx, gg):
+        transpose, scale = ctx.cfg
+        return PackWeight.apply(gg, transpose, scale), None, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------- the three GEMMs
+class ConvFwd(Function):
+    @staticmethod
+    def forward(ctx, x, wp, bias, g: Geom, act, alpha, gain):
+        require_cuda(x, wp, bias)
+        x = nhwc(x)
+        _check(x, (g.N, g.C, g.H, g.W), "conv forward input")
+        _check(wp, (g.kh * g.kw, g.K, g.C), "conv forward packed weight")
+        y = _fwd(x, wp, g, bias=bias, act=act, alpha=alpha, gain=gain)
+        ctx.g, ctx.act, ctx.alpha, ctx.gain, ctx.has_bias = g, act, alpha, gain, bias is not None
+        ctx.save_for_backward(x, wp, y if act != _lib.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wp, out = ctx.saved_tensors
+        g = ctx.g
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
+        gb = None
+        if ctx.act != _lib.ACT_NONE:
+            gy, gb = FusedLeakyReLUFunctionBackward.apply(gy, out, want_bias, ctx.alpha, ctx.gain)
+        elif want_bias:
+            gb = gy.sum(dim=(0, 2, 3))
+        gx = ConvDgrad.apply(gy, wp, g) if ctx.needs_input_grad[0] else None
+        gw = ConvWgrad.apply(x, gy, g) if ctx.needs_input_grad[1] else None
+        return gx, gw, (gb if want_bias else None), None, None, None, None
+
+
+class ConvDgrad(Function):
+    @staticmethod
+    def forward(ctx, dy, wp, g: Geom):
+        require_cuda(dy, wp)
+        dy = nhwc(dy)
+        _check(dy, (g.N, g.K, g.OH, g.OW), "conv dgrad input")
+        _check(wp, (g.kh * g.kw, g.K, g.C), "conv dgrad packed weight")
+        ctx.g = g
+        ctx.save_for_backward(dy, wp)
+        return _dgrad(dy, wp, g)
+
+    @staticmethod
+    def backward(ctx, gg):
+        dy, wp = ctx.saved_tensors
+        g = ctx.g
+        g_dy = ConvFwd.apply(gg, wp, None, g, _lib.ACT_NONE, 0.2, 1.0) if ctx.needs_input_grad[0] else None
+        g_wp = ConvWgrad.apply(gg, dy, g) if ctx.needs_input_grad[1] else None
+        return g_dy, g_wp, None
+
+
+class ConvWgrad(Function):
+    @staticmethod
+    def forward(ctx, x, dy, g: Geom):
+        require_cuda(x, dy)
+        x, dy = nhwc(x), nhwc(dy)
+        _check(x, (g.N, g.C, g.H, g.W), "conv wgrad input")
+        _check(dy, (g.N, g.K, g.OH, g.OW), "conv wgrad output-gradient")
+        ctx.g = g
+        ctx.save_for_backward(x, dy)
+        return _wgrad(x, dy, g)
+
+    @staticmethod
+    def backward(ctx, G):
+        x, dy = ctx.saved_tensors
+        g = ctx.g
+        G = G.contiguous()
+        g_x = ConvDgrad.apply(dy, G, g) if ctx.needs_input_grad[0] else None
+        g_dy = ConvFwd.apply(x, G, None, g, _lib.ACT_NONE, 0.2, 1.0) if ctx.needs_input_grad[1] else None
+        return g_x, g_dy, None
+
+
+def conv2d(x, wp, bias=None, *, K, kh, kw, stride=1, pad=0, act=False, alpha=0.2, gain=2 ** 0.5):
+    """y = [lrelu](conv(x, w) + bias) with packed weights (see PackWeight)."""
+    g = Geom.forward(x.shape, K, kh, kw, stride, pad)
+    return ConvFwd.apply(x, wp, bias, g, _lib.ACT_LRELU if act else _lib.ACT_NONE, alpha, gain if act else 1.0)
+
+
+def conv_transpose2d(x, wp, *, C_out, kh, kw, stride=1, pad=0):
+    """y = conv_transpose2d(x, w); wp is the packed weight of the conv this is the adjoint of:
+    (taps, Cin_of_x, C_out)."""
+    g = Geom.transposed(x.shape, C_out, kh, kw, stride, pad)
+    return ConvDgrad.apply(x, wp, g)
+
+
+# --------------------------------------------------------------------------- modulated convolutions
+def _umma_shape_ok(g: Geom) -> bool:
+    return _lib.umma_enabled() and g.C % 32 == 0 and g.K % 32 == 0
+
+
+class ModConv(Function):
+    """out = gain * lrelu(d[n,k] * conv(s[n,c] * x, w)[n,k] + bias[k])   (same resolution).
+
+    Restates ModulatedConv2d.forward's non-resampling branch + FusedLeakyReLU
+    (stylegan2/model.py:236-248,271-275,375).  ``d`` may be None (demodulate=False) and
+    ``bias`` None with ``act=False`` (plain modulated conv, e.g. ToRGB)."""
+
+    @staticmethod
+    def forward(ctx, x, s, d, wp, bias, g: Geom, act, alpha, gain):
+        require_cuda(x, s, d, wp, bias)
+        x = nhwc(x)
+        s = s.contiguous()
+        d = d.contiguous() if d is not None else None
+        _check(x, (g.N, g.C, g.H, g.W), "modconv input")
+        xm = None
+        code = _lib.ACT_LRELU if act else _lib.ACT_NONE
+        if _umma_shape_ok(g) and DEFAULT_IMPL != _lib.IMPL_SIMT:
+            xm = torch.empty_like(x)
+            _lib.call("ideas_scale_channels", ptr(xm), ptr(x), ptr(s), g.N, g.H * g.W, g.C, stream_ptr(x))
+            out = _fwd(xm, wp, g, out_scale=d, bias=bias, act=code, alpha=alpha, gain=gain)
+        else:
+            out = _fwd(x, wp, g, in_scale=s, out_scale=d, bias=bias, act=code, alpha=alpha, gain=gain,
+                       impl=_lib.IMPL_SIMT)
+        ctx.g, ctx.act, ctx.alpha, ctx.gain = g, act, alpha, gain
+        # the bias is a leaf parameter: save a private copy, never the leaf (train.py:209-216 steps the
+        # optimiser between two backwards over this graph)
+        ctx.save_for_backward(x, s, d, wp, bias.clone() if bias is not None else None, out, xm)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, s, d, wp, bias, out, xm = ctx.saved_tensors
+        g = ctx.g
+        gy = nhwc(gy)
+        st = stream_ptr(gy)
+        P = g.OH * g.OW
+        gb = gd = None
+        if ctx.act:
+            g1d = torch.empty_like(out)
+            gsum = torch.zeros((g.N, g.K), device=gy.device, dtype=gy.dtype)
+            dotz = torch.zeros_like(gsum)
+            _lib.call("ideas_modconv_act_backward", ptr(g1d), ptr(gsum), ptr(dotz), ptr(gy), ptr(out), ptr(d),
+                      float(ctx.alpha), float(ctx.gain), g.N, P, g.K, st)
+            if bias is not None:
+                gb = gsum.sum(0)
+            if d is not None:
+                gd = (dotz - (bias * gsum if bias is not None else 0.0)) / d
+        else:
+            if d is not None:
+                # out = d*u (+bias): dL/dd = sum_p gy*u = sum_p gy*(out-bias)/d ; g1d = gy*d
+                g1d = torch.empty_like(out)
+                dot = torch.zeros((g.N, g.K), device=gy.device, dtype=gy.dtype)
+                _lib.call("ideas_channel_dot", ptr(dot), ptr(g1d), ptr(out), ptr(gy), ptr(d), g.N, P, g.K, st)
+                gsum = gy.sum(dim=(2, 3))
+                gd = (dot - (bias * gsum if bias is not None else 0.0)) / d
+                if bias is not None:
+                    gb = gsum.sum(0)
+            else:
+                g1d = gy
+                if bias is not None:
+                    gb = gy.sum(dim=(0, 2, 3))
+        gx = gs = gw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dxm = _dgrad(g1d, wp, g)
+            gx = torch.empty_like(x)
+            gs = torch.zeros((g.N, g.C), device=gy.device, dtype=gy.dtype)
+            _lib.call("ideas_channel_dot", ptr(gs), ptr(gx), ptr(x), ptr(dxm), ptr(s), g.N, g.H * g.W, g.C, st)
+        if ctx.needs_input_grad[3]:
+            gw = _wgrad(xm, g1d, g) if xm is not None else _wgrad(x, g1d, g, in_scale=s, impl=_lib.IMPL_SIMT)
+        return gx, gs, gd, gw, gb, None, None, None, None
+
+
+class ModConvUp(Function):
+    """out = gain * lrelu(blur(d * conv_transpose(s * x, w, stride 2)) + bias)  -- the upsampling
+    branch of ModulatedConv2d + its Blur + FusedLeakyReLU (stylegan2/model.py:250-261,375).
+    ``wp`` is (taps, Cin, Cout): the packed weight of the stride-2 conv this is the adjoint of.
+    ``g`` is that conv's geometry (x here plays its output-gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, s, d, wp, blur_kernel, blur_pad, bias, g: Geom, act, alpha, gain):
+        require_cuda(x, s, d, wp, blur_kernel, bias)
+        if act and bias is None:
+            raise RuntimeError("modconv-up: the fused activation needs a bias")
+        x = nhwc(x)
+        s = s.contiguous()
+        d = d.contiguous() if d is not None else None
+        _check(x, (g.N, g.K, g.OH, g.OW), "modconv-up input")
+        xm = None
+        if _umma_shape_ok(g) and DEFAULT_IMPL != _lib.IMPL_SIMT:
+            xm = torch.empty_like(x)
+            _lib.call("ideas_scale_channels", ptr(xm), ptr(x), ptr(s), g.N, g.OH * g.OW, g.K, stream_ptr(x))
+            u = _dgrad(xm, wp, g, in_scale=d)
+        else:
+            u = _dgrad(x, wp, g, in_scale=d, out_scale=s, impl=_lib.IMPL_SIMT)
+        kernel = blur_kernel.contiguous()
+        out = _upfirdn_run(u, kernel, (1, 1), (1, 1), blur_pad, bias=bias if act else None, alpha=alpha, gain=gain)
+        ctx.g, ctx.act, ctx.alpha, ctx.gain, ctx.blur_pad = g, act, alpha, gain, blur_pad
+        ctx.save_for_backward(x, s, d, wp, kernel, u, out if act else None, xm)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, s, d, wp, kernel, u, out, xm = ctx.saved_tensors
+        g = ctx.g
+        gy = nhwc(gy)
+        st = stream_ptr(gy)
+        gb = None
+        if ctx.act:
+            g1, gb = FusedLeakyReLUFunctionBackward.apply(gy, out, ctx.needs_input_grad[6], ctx.alpha, ctx.gain)
+        else:
+            g1 = gy
+        g_pad = _grad_pad((u.shape[2], u.shape[3]), (gy.shape[2], gy.shape[3]), kernel.shape, (1, 1), (1, 1),
+                          ctx.blur_pad)
+        gu = _upfirdn_run(g1, torch.flip(kernel, [0, 1]), (1, 1), (1, 1), g_pad)
+        gd = None
+        if d is not None:
+            gud = torch.empty_like(gu)
+            dot = torch.zeros((g.N, g.C), device=gy.device, dtype=gy.dtype)
+            _lib.call("ideas_channel_dot", ptr(dot), ptr(gud), ptr(u), ptr(gu), ptr(d), g.N, g.H * g.W, g.C, st)
+            gd = dot / d
+        else:
+            gud = gu
+        gx = gs = gw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dxm = _fwd(gud, wp, g)                                  # adjoint of the transposed conv
+            gx = torch.empty_like(x)
+            gs = torch.zeros((g.N, g.K), device=gy.device, dtype=gy.dtype)
+            _lib.call("ideas_channel_dot", ptr(gs), ptr(gx), ptr(x), ptr(dxm), ptr(s), g.N, g.OH * g.OW, g.K, st)
+        if ctx.needs_input_grad[3]:
+            gw = _wgrad(gud, xm, g) if xm is not None else _wgrad(gud, x, g, out_scale=s, impl=_lib.IMPL_SIMT)
+        return gx, gs, gd, gw, None, None, (gb if (ctx.act and ctx.needs_input_grad[6]) else None), None, None, None, None

@@ -1,0 +1,222 @@
+"""One IDEAS training iteration on the B200 networks, single- or multi-GPU.
+
+Mirrors the loop body of the reference's train.py:33-221 statement for statement: D phase
+(:48-102), lazy R1 every ``d_reg_every`` iterations (:105-129), G/E/Ex phase with its two
+backwards over one retained graph (:135-216), EMA (:218-221); the three Adam optimisers
+and their lazy-regularisation-corrected hyper-parameters are those of train.py:417-432.
+
+Data parallelism (new; the reference is single-process): every rank runs the
+same step on its own slice of the batch with its own Z / T2 / crops; gradients are averaged
+with ONE flat NCCL all-reduce per optimiser step, issued from an ``optimizer.step`` pre-hook
+so the training loop itself never mentions the process group.  Stock DDP is not used: the
+second backward without a forward (train.py:214-216) is outside its contract.
+"""
+from __future__ import annotations
+
+import argparse
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import optim
+from torch.nn import functional as F
+
+from .models import init_model
+from .utils import (accumulate, d_logistic_loss, d_r1_loss, draw_crops, g_nonsaturating_loss, patchify_image,
+                    requires_grad)
+
+NET_CLASSES = [("E", "DisentanglementEncoder"), ("G", "Generator"), ("Gstru", "StructureGenerator"),
+               ("Ex", "TensorExtractor"), ("Dreal", "ImageLevelDiscriminator"),
+               ("Dco", "CooccurenceDiscriminator"), ("Ddist", "DistributionDiscriminator")]
+EMA_KEYS = ("E", "G", "Gstru", "Ex")
+
+
+def default_args(**overrides) -> argparse.Namespace:
+    """Hyper-parameters with the reference's defaults (train.py:331-370)."""
+    d = dict(N=1, lambda_Ex=10.0, lr=0.002, batch_size=1, image_size=256, real_r1=10.0, texture_r1=1.0, dist_r1=1.0,
+             ref_crop=4, n_crop=8, d_reg_every=16, channel=32, channel_multiplier=1, structure_channel=8,
+             texture_channel=2048, num_iters=80000, start_iter=0, blur_kernel=(1, 3, 3, 1))
+    d.update(overrides)
+    return argparse.Namespace(**d)
+
+
+class FlatGradAllReduce:
+    """Average the gradients of one optimiser's parameters across ranks with a single
+    all-reduce on a flat fp32 bucket (d-group 182 MB, g-group 257 MB, ex-group 1.5 MB)."""
+
+    def __init__(self, params: List[torch.Tensor], group=None):
+        self.params = [p for p in params]
+        self.group = group
+        self.flat: Optional[torch.Tensor] = None
+        self.calls = 0
+
+    def __call__(self, optimizer=None, args=None, kwargs=None):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        ps = [p for p in self.params if p.grad is not None]
+        if not ps:
+            return
+        n = sum(p.numel() for p in ps)
+        if self.flat is None or self.flat.numel() != n or self.flat.device != ps[0].device:
+            self.flat = torch.empty(n, dtype=torch.float32, device=ps[0].device)
+        off = 0
+        views = []
+        for p in ps:
+            v = self.flat[off:off + p.numel()].view_as(p.grad)
+            views.append(v)
+            off += p.numel()
+        torch._foreach_copy_(views, [p.grad for p in ps])
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(dist.get_world_size(self.group))
+        torch._foreach_copy_([p.grad for p in ps], views)
+        self.calls += 1
+
+
+class Trainer:
+    """The ``trainer`` dict of train.py:390-432 as an object (``trainer[key]`` still works)."""
+
+    def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
+                 states: Optional[Dict[str, dict]] = None):
+        self.args = args
+        self.device = torch.device(device)
+        if seed is not None:
+            torch.manual_seed(seed)
+        self.nets: Dict[str, torch.nn.Module] = {}
+        for key, cls in NET_CLASSES:                                    # same construction order as train.py:390-399
+            self.nets[key] = init_model(cls, args)
+        for key in EMA_KEYS:                                            # train.py:400-414
+            cls = dict(NET_CLASSES)[key]
+            self.nets[key + "_ema"] = init_model(cls, args).eval()
+        if states is not None:
+            for k, sd in states.items():
+                self.nets[k].load_state_dict(sd)
+        for k in self.nets:
+            self.nets[k].to(self.device)
+        for key in EMA_KEYS:
+            accumulate(self.nets[key + "_ema"], self.nets[key], 0)
+        P = lambda *ks: [p for k in ks for p in self.nets[k].parameters()]  # noqa: E731
+        fused = bool(fused_adam and self.device.type == "cuda")
+        self.g_optim = optim.Adam(P("E", "G", "Gstru"), lr=args.lr, betas=(0.0, 0.99), fused=fused)
+        self.ex_optim = optim.Adam(P("Ex"), lr=args.lr, betas=(0.0, 0.99), fused=fused)
+        r = args.d_reg_every / (args.d_reg_every + 1)
+        self.d_optim = optim.Adam(P("Dreal", "Dco", "Ddist"), lr=args.lr * r, betas=(0.0 ** r, 0.99 ** r), fused=fused)
+        self.reducers = {}
+        for name, opt in (("g", self.g_optim), ("ex", self.ex_optim), ("d", self.d_optim)):
+            red = FlatGradAllReduce([p for grp in opt.param_groups for p in grp["params"]])
+            opt.register_step_pre_hook(red)
+            self.reducers[name] = red
+        self.accum = 0.5 ** (32 / (10 * 1000))                          # train.py:30
+
+    def __getitem__(self, key):
+        if key in self.nets:
+            return self.nets[key]
+        return {"g_optim": self.g_optim, "ex_optim": self.ex_optim, "d_optim": self.d_optim}[key]
+
+    def keys(self):
+        return list(self.nets) + ["g_optim", "ex_optim", "d_optim"]
+
+    def broadcast_parameters(self, src: int = 0):
+        """Make every rank start from rank ``src``'s weights (one flat broadcast per network)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        for net in self.nets.values():
+            ps = [p.data for p in net.parameters()]
+            flat = torch.cat([p.reshape(-1) for p in ps])
+            dist.broadcast(flat, src)
+            off = 0
+            for p in ps:
+                p.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+
+    # -------------------------------------------------------------------------------------
+    def _rand_like_Z(self, S, draws, key):
+        if draws is not None and key in draws:
+            return draws[key].to(self.device)
+        # train.py:60-61 draws on the CPU generator and copies; kept so seeded runs match the reference
+        return torch.rand(size=(S.shape[0], self.args.N, S.shape[2], S.shape[3]), dtype=torch.float).to(self.device) * 2 - 1
+
+    def _rand_like_T(self, T, draws, key):
+        if draws is not None and key in draws:
+            return draws[key].to(self.device)
+        return torch.rand_like(T) * 2 - 1
+
+    def step(self, X: torch.Tensor, iter_idx: int, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        """One iteration on batch X (already on the device).  Returns the loss tensors (device
+        scalars; ``.item()`` them only when logging, as train.py:224-232 does)."""
+        a, t = self.args, self.nets
+        H, W = X.shape[2], X.shape[3]
+        crops = (lambda key, n: draws[key] if (draws is not None and key in draws) else draw_crops(n, H, W))
+        loss = {}
+        # ---------------- discriminators (train.py:48-102)
+        for k in EMA_KEYS:
+            requires_grad(t[k], False)
+        for k in ("Dreal", "Dco", "Ddist"):
+            requires_grad(t[k], True)
+        S1, T1 = t["E"](X)
+        Z = self._rand_like_Z(S1, draws, "Z_d")
+        S2 = t["Gstru"](Z)
+        T2 = self._rand_like_T(T1, draws, "T2_d")
+        hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
+        fake_pred = t["Dreal"](torch.cat((hat_X1, hat_X2, hat_X3), 0))
+        real_pred = t["Dreal"](X)
+        D_real_loss = d_logistic_loss(real_pred, fake_pred)
+        fake_patch = patchify_image(hat_X2, a.n_crop, crops=crops("fake_crops_d", a.n_crop))
+        real_patch = patchify_image(X, a.n_crop, crops=crops("real_crops_d", a.n_crop))
+        ref_patch = patchify_image(X, a.ref_crop * a.n_crop, crops=crops("ref_crops_d", a.ref_crop * a.n_crop))
+        fake_texture_pred, ref_input = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
+        real_texture_pred, _ = t["Dco"](real_patch, ref_input=ref_input)
+        D_texture_loss = d_logistic_loss(real_texture_pred, fake_texture_pred)
+        D_dist_loss = d_logistic_loss(t["Ddist"](T2), t["Ddist"](T1))
+        loss.update(D_real_loss=D_real_loss, D_texture_loss=D_texture_loss, D_dist_loss=D_dist_loss)
+        self.d_optim.zero_grad()
+        (D_real_loss + D_texture_loss + D_dist_loss).backward()
+        self.d_optim.step()
+        # ---------------- lazy R1 (train.py:105-129)
+        if iter_idx % a.d_reg_every == 0:
+            Xr = X.detach().requires_grad_(True)
+            r1_real = d_r1_loss(t["Dreal"](Xr), Xr)
+            rp = real_patch.detach().requires_grad_(True)
+            pred, _ = t["Dco"](rp, ref_patch, ref_batch=a.ref_crop)
+            r1_tex = d_r1_loss(pred, rp)
+            T2r = T2.detach().requires_grad_(True)
+            r1_dist = d_r1_loss(t["Ddist"](T2r), T2r)
+            self.d_optim.zero_grad()
+            r1_sum = a.real_r1 / 3 * r1_real * a.d_reg_every
+            r1_sum = r1_sum + a.texture_r1 / 3 * r1_tex * a.d_reg_every
+            r1_sum = r1_sum + a.dist_r1 / 3 * r1_dist * a.d_reg_every
+            r1_sum.backward()
+            self.d_optim.step()
+            loss.update(D_real_r1_loss=r1_real, D_texture_r1_loss=r1_tex, D_dist_r1_loss=r1_dist)
+        # ---------------- encoder / generators / extractor (train.py:135-216)
+        for k in EMA_KEYS:
+            requires_grad(t[k], True)
+        for k in ("Dreal", "Dco", "Ddist"):
+            requires_grad(t[k], False)
+        S1, T1 = t["E"](X)
+        Z = self._rand_like_Z(S1, draws, "Z_g")
+        S2 = t["Gstru"](Z)
+        T2 = self._rand_like_T(T1, draws, "T2_g")
+        hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
+        G_rec_loss = F.l1_loss(hat_X1, X)
+        G_real_loss = g_nonsaturating_loss(t["Dreal"](torch.cat((hat_X1, hat_X2, hat_X3), 0)))
+        E_dist_loss = g_nonsaturating_loss(t["Ddist"](T1))
+        fake_patch = patchify_image(hat_X2, a.n_crop, crops=crops("fake_crops_g", a.n_crop))
+        ref_patch = patchify_image(X, a.ref_crop * a.n_crop, crops=crops("ref_crops_g", a.ref_crop * a.n_crop))
+        fake_patch_pred, _ = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
+        G_texture_loss = g_nonsaturating_loss(fake_patch_pred)
+        container = hat_X3 if iter_idx > a.num_iters * 0.8 else hat_X2
+        hat_S2, _ = t["E"](container)
+        E_stru_loss = F.l1_loss(hat_S2, S2)
+        Ex_loss = F.l1_loss(t["Ex"](hat_S2), Z)
+        Loss_total = (G_rec_loss + G_texture_loss + 2 * G_real_loss) + (E_dist_loss + E_stru_loss) + a.lambda_Ex * Ex_loss
+        self.g_optim.zero_grad()
+        Loss_total.backward(retain_graph=True)
+        self.g_optim.step()
+        self.ex_optim.zero_grad()
+        Ex_loss.backward()
+        self.ex_optim.step()
+        for k in EMA_KEYS:
+            accumulate(t[k + "_ema"], t[k], self.accum)
+        loss.update(G_rec_loss=G_rec_loss, G_real_loss=G_real_loss, G_texture_loss=G_texture_loss,
+                    E_dist_loss=E_dist_loss, E_stru_loss=E_stru_loss, Ex_loss=Ex_loss, Loss_total=Loss_total)
+        return loss

@@ -48,7 +48,12 @@ _PROTOTYPES = {
     "ideas_bits_decode": [_P, _P, c_int, c_int, c_int, _P],
     "ideas_bits_count_errors": [_P, _P, _P, c_int64, _P],
 }
-EXPORTS = sorted(list(_PROTOTYPES) + ["ideas_last_error"])
+EXPORTS = sorted(list(_PROTOTYPES) + ["ideas_last_error", "ideas_launch_count"])
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far in this process."""
+    return int(lib().ideas_launch_count())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -104,6 +109,8 @@ def lib() -> ctypes.CDLL:
             fn.restype = c_int
         L.ideas_last_error.argtypes = []
         L.ideas_last_error.restype = ctypes.c_char_p
+        L.ideas_launch_count.argtypes = []
+        L.ideas_launch_count.restype = ctypes.c_ulonglong
         _lib = L
     return _lib
 

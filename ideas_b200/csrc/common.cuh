@@ -11,6 +11,7 @@ namespace ideas {
 
 // thread-local last error (ideas_last_error); defined in elementwise.cu
 void set_error(const char* fmt, ...);
+void count_launch();
 
 inline int cuda_fail(cudaError_t e, const char* what) {
   set_error("%s: %s", what, cudaGetErrorString(e));
@@ -25,8 +26,11 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     }                                       \
   } while (0)
 
+// every kernel launch of the library goes through this macro: it counts the launch
+// (ideas_launch_count, reported by bench.py as gpu_launches) and checks for a launch error
 #define IDEAS_CHECK_LAUNCH(name)                                  \
   do {                                                            \
+    ideas::count_launch();                                        \
     cudaError_t e__ = cudaGetLastError();                         \
     if (e__ != cudaSuccess) return ideas::cuda_fail(e__, name);   \
   } while (0)

@@ -4,9 +4,14 @@
 // (out+skip)/sqrt(2) of models.py:178,227.  All HBM-bound, 128-bit vectorised.
 #include "common.cuh"
 
+#include <atomic>
+
 namespace ideas {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -117,6 +122,7 @@ using namespace ideas;
 
 extern "C" int ideas_abi_version(void) { return 1; }
 extern "C" const char* ideas_last_error(void) { return g_err; }
+extern "C" unsigned long long ideas_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ideas_device_cc(void) {
   int dev = 0, major = 0, minor = 0;

@@ -1,0 +1,309 @@
+"""GPU parity of the op layer: the CUDA kernels, reached through the C ABI
+(libideas_b200.so via ctypes), against the CPU oracle (oracle/functional.py) and the
+reference-generated goldens (tests/golden/ops.pt).  Tolerance: 1e-3 fp32 relative
+(BASELINE.json north_star); the fp32 SIMT path is held to 2e-5, elementwise ops to exact."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import functional as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north-star tolerance (tcgen05 / TF32 paths)
+TOL_FP32 = 3e-5     # fp32 FFMA paths
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+@pytest.fixture(scope="module")
+def ops(golden_dir):
+    return torch.load(os.path.join(golden_dir, "ops.pt"))
+
+
+@pytest.fixture(scope="module")
+def op():
+    from ideas_b200.stylegan2 import op as mod
+    return mod
+
+
+# ------------------------------------------------------------------ A3 fused bias + leaky ReLU
+def test_fused_leaky_relu_forward_golden(ops, op):
+    for key in ("flrelu", "flrelu_2d"):
+        c = ops[key]
+        got = op.fused_leaky_relu(c["x"].cuda(), c["bias"].cuda())
+        assert torch.equal(got.cpu(), c["out"]), key           # same fp32 op order => bit-exact
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 7, 9), (3, 8, 16, 16), (4, 64), (2, 128, 33, 31), (1, 3, 5, 5, 2), (0, 8, 4, 4)])
+def test_fused_leaky_relu_first_and_second_order(op, shape):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(*shape, generator=g)
+    b = torch.randn(shape[1], generator=g)
+    gy = torch.randn(*shape, generator=g)
+    gg = torch.randn(*shape, generator=g)
+
+    def run(fn, dev):
+        xx = x.to(dev).requires_grad_(True)
+        bb = b.to(dev).requires_grad_(True)
+        out = fn(xx, bb)
+        gx, gb = torch.autograd.grad(out, [xx, bb], gy.to(dev), create_graph=True)
+        # second order: d/d(gy-like) path through the saved mask (what R1 exercises)
+        (ggx,) = torch.autograd.grad((gx * gg.to(dev)).sum() + gb.sum(), [xx], allow_unused=True)
+        return out, gx, gb, ggx
+
+    o_c, gx_c, gb_c, _ = run(lambda a, c: O.fused_leaky_relu(a, c), "cpu")
+    o_g, gx_g, gb_g, ggx_g = run(lambda a, c: op.fused_leaky_relu(a, c), "cuda")
+    assert torch.equal(o_g.cpu(), o_c.detach())
+    if x.numel():
+        assert rel(gx_g, gx_c) <= 1e-6
+        assert rel(gb_g, gb_c) <= 1e-5
+    # piecewise linear: the second derivative w.r.t. x is identically zero
+    assert ggx_g is None or float(ggx_g.abs().max()) == 0.0 if x.numel() else True
+
+
+def test_fused_leaky_relu_double_backward_matches_oracle(op):
+    # R1: grad of (dL/dx) w.r.t. the upstream gradient -- fused_act.py:43-49
+    g = torch.Generator().manual_seed(2)
+    x, b = torch.randn(2, 8, 6, 6, generator=g), torch.randn(8, generator=g)
+
+    def run(fn, dev):
+        xx = x.to(dev)
+        gy = torch.randn(2, 8, 6, 6, generator=torch.Generator().manual_seed(3)).to(dev).requires_grad_(True)
+        xin = xx.clone().requires_grad_(True)
+        out = fn(xin, b.to(dev))
+        (gx,) = torch.autograd.grad(out, xin, gy, create_graph=True)
+        (ggy,) = torch.autograd.grad(gx.pow(2).sum(), gy)
+        return ggy
+
+    assert rel(run(op.fused_leaky_relu, "cuda"), run(O.fused_leaky_relu, "cpu")) <= 1e-6
+
+
+def test_native_bias_act_codes(op):
+    """The C entry point honours every act*10+grad code of fused_bias_act_kernel.cu:36-47."""
+    from ideas_b200.stylegan2.op.fused_act import _bias_act
+    g = torch.Generator().manual_seed(4)
+    x, b, r = torch.randn(2, 8, 4, 4, generator=g), torch.randn(8, generator=g), torch.randn(2, 8, 4, 4, generator=g)
+    for act, grad in [(1, 0), (1, 1), (1, 2), (3, 0), (3, 1), (3, 2)]:
+        want = O.bias_act(x, b, r, act, grad, 0.2, 1.5)
+        xc = x.cuda().contiguous(memory_format=torch.channels_last)
+        rc = r.cuda().contiguous(memory_format=torch.channels_last)
+        got = _bias_act(xc, b.cuda(), rc, act, grad, 0.2, 1.5)
+        assert torch.equal(got.cpu(), want), (act, grad)
+
+
+def test_ops_refuse_cpu_tensors(op):
+    with pytest.raises(RuntimeError):
+        op.fused_leaky_relu(torch.randn(1, 4, 2, 2), torch.zeros(4))
+    with pytest.raises(RuntimeError):
+        op.upfirdn2d(torch.randn(1, 4, 8, 8), O.make_kernel([1, 3, 3, 1]), pad=(2, 1))
+
+
+# ------------------------------------------------------------------ A4 upfirdn2d
+def test_upfirdn2d_golden_all_modes(ops, op):
+    for c in ops["upfirdn2d"]:
+        got = op.upfirdn2d(c["x"].cuda(), c["kernel"].cuda(), up=c["up"], down=c["down"], pad=tuple(c["pad"]))
+        assert rel(got, c["out"]) <= 2e-6, c["name"]
+
+
+@pytest.mark.parametrize("C,H,W,pad,gain", [(8, 16, 16, (2, 2), 1), (128, 33, 33, (1, 1), 4), (4, 9, 31, (2, 1), 1),
+                                            (12, 64, 64, (1, 1), 1), (3, 17, 13, (2, 2), 1), (64, 257, 257, (1, 1), 4)])
+def test_blur_fwd_bwd_double_bwd(op, C, H, W, pad, gain):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, C, H, W, generator=g)
+    k = O.make_kernel([1, 3, 3, 1]) * gain
+
+    def run(fn, dev):
+        xx = x.to(dev).requires_grad_(True)
+        out = fn(xx, k.to(dev), pad=pad)
+        gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(6)).to(dev).requires_grad_(True)
+        (gx,) = torch.autograd.grad(out, xx, gy, create_graph=True)
+        (ggy,) = torch.autograd.grad(gx.pow(2).sum(), gy)
+        return out, gx, ggy
+
+    for a, b in zip(run(op.upfirdn2d, "cuda"), run(O.upfirdn2d, "cpu")):
+        assert rel(a, b) <= 5e-6
+
+
+def test_blur_bias_act_fused_epilogue(op):
+    g = torch.Generator().manual_seed(7)
+    x, b = torch.randn(2, 16, 12, 12, generator=g), torch.randn(16, generator=g)
+    k = O.make_kernel([1, 3, 3, 1]) * 4
+
+    def run(dev, fused):
+        xx, bb = x.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+        if fused:
+            out = op.blur_bias_act(xx, k.to(dev), (1, 1), bb)
+        else:
+            out = O.fused_leaky_relu(O.upfirdn2d(xx, k, pad=(1, 1)), bb)
+        gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(8)).to(dev)
+        gx, gb = torch.autograd.grad(out, [xx, bb], gy)
+        return out, gx, gb
+
+    for a, c in zip(run("cuda", True), run("cpu", False)):
+        assert rel(a, c) <= 1e-5
+
+
+def test_upfirdn2d_empty_and_identity(op):
+    k1 = torch.ones(1, 1).cuda()
+    x = torch.randn(1, 2, 5, 5).cuda()
+    assert torch.equal(op.upfirdn2d(x, k1), x)
+    assert op.upfirdn2d(torch.zeros(0, 4, 5, 5).cuda(), O.make_kernel([1, 3, 3, 1]).cuda(), pad=(2, 1)).shape == (0, 4, 5, 5)
+
+
+# ------------------------------------------------------------------ A5 convolution family
+CONV_CASES = [
+    # N, C, K, H, W, k, stride, pad
+    (2, 3, 32, 16, 16, 1, 1, 0), (2, 32, 64, 18, 18, 3, 1, 0), (2, 64, 64, 17, 17, 3, 2, 0), (1, 8, 128, 16, 16, 3, 1, 1),
+    (2, 33, 7, 9, 11, 3, 1, 1), (2, 64, 32, 15, 15, 1, 2, 0), (3, 96, 48, 2, 2, 2, 1, 0), (2, 128, 3, 8, 8, 1, 1, 0),
+    (1, 128, 128, 33, 33, 3, 2, 0), (2, 256, 512, 8, 8, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_conv2d_fwd_dgrad_wgrad(case, impl):
+    from ideas_b200 import _lib
+    from ideas_b200.stylegan2.op import conv2d as C
+    N, Ci, K, H, W, k, stride, pad = case
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(K, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5
+    b = torch.randn(K, generator=g)
+    old = C.set_default_impl(_lib.IMPL_SIMT if impl == "simt" else _lib.IMPL_AUTO)
+    try:
+        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        want = O.fused_leaky_relu(F.conv2d(xr, wr, None, stride, pad), br)
+        gy = torch.randn(want.shape, generator=g)
+        wg = torch.autograd.grad(want, [xr, wr, br], gy)
+        xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+        wp = C.PackWeight.apply(wc, False, 1.0)
+        got = C.conv2d(xc, wp, bc, K=K, kh=k, kw=k, stride=stride, pad=pad, act=True)
+        gg = torch.autograd.grad(got, [xc, wc, bc], gy.cuda())
+        tol = TOL_FP32 if impl == "simt" else TOL
+        assert rel(got, want) <= tol
+        for a, c in zip(gg, wg):
+            assert rel(a, c) <= tol * 3
+    finally:
+        C.set_default_impl(old)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 8, 7, 7, 1, 2), (2, 64, 32, 16, 16, 3, 2), (1, 32, 32, 5, 6, 3, 1), (2, 128, 64, 16, 16, 1, 2)])
+def test_conv_transpose2d(case):
+    from ideas_b200.stylegan2.op import conv2d as C
+    N, Ci, Co, H, W, k, stride = case
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Ci, Co, k, k, generator=g) / (Ci * k * k) ** 0.5
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    want = F.conv_transpose2d(xr, wr, stride=stride)
+    gy = torch.randn(want.shape, generator=g)
+    wg = torch.autograd.grad(want, [xr, wr], gy)
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    wp = C.PackWeight.apply(wc, False, 1.0)
+    got = C.conv_transpose2d(xc, wp, C_out=Co, kh=k, kw=k, stride=stride, pad=0)
+    gg = torch.autograd.grad(got, [xc, wc], gy.cuda())
+    assert rel(got, want) <= TOL
+    for a, c in zip(gg, wg):
+        assert rel(a, c) <= TOL * 3
+
+
+def test_conv_second_order_r1_style():
+    """R1 differentiates dD/dx w.r.t. the weights: conv double-backward (utils.py:112-118)."""
+    from ideas_b200.stylegan2.op import conv2d as C
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 8, 10, 10, generator=g)
+    w1 = torch.randn(16, 8, 3, 3, generator=g) / 8.5
+    w2 = torch.randn(4, 16, 3, 3, generator=g) / 12
+    b1 = torch.randn(16, generator=g)
+
+    def oracle():
+        xr = x.clone().requires_grad_(True)
+        a, c = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+        bb = b1.clone().requires_grad_(True)
+        y = F.conv2d(O.fused_leaky_relu(F.conv2d(xr, a, None, 1, 1), bb), c, None, 2, 0)
+        (gx,) = torch.autograd.grad(y.sum(), xr, create_graph=True)
+        pen = gx.pow(2).sum()
+        return (pen,) + torch.autograd.grad(pen, [a, c, bb])
+
+    def ours():
+        xr = x.cuda().requires_grad_(True)
+        a, c = w1.cuda().requires_grad_(True), w2.cuda().requires_grad_(True)
+        bb = b1.cuda().requires_grad_(True)
+        h = C.conv2d(xr, C.PackWeight.apply(a, False, 1.0), bb, K=16, kh=3, kw=3, stride=1, pad=1, act=True)
+        y = C.conv2d(h, C.PackWeight.apply(c, False, 1.0), None, K=4, kh=3, kw=3, stride=2, pad=0)
+        (gx,) = torch.autograd.grad(y.sum(), xr, create_graph=True)
+        pen = gx.pow(2).sum()
+        return (pen,) + torch.autograd.grad(pen, [a, c, bb])
+
+    for a, c in zip(ours(), oracle()):
+        assert rel(a, c) <= TOL
+
+
+# ------------------------------------------------------------------ A1/A2 modulated convolution
+def _load_modconv(c):
+    from ideas_b200.stylegan2 import model as M
+    sd = c["sd"]
+    cout, cin = sd["weight"].shape[1], sd["weight"].shape[2]
+    m = M.ModulatedConv2d(cin, cout, c["k"], sd["modulation.weight"].shape[1], demodulate=c["demodulate"],
+                          upsample=c["upsample"], downsample=c["downsample"])
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def test_modulated_conv_golden(ops):
+    for c in ops["modconv"]:
+        m = _load_modconv(c)
+        x = c["x"].cuda().requires_grad_(True)
+        st = c["style"].cuda().requires_grad_(True)
+        out = m(x, st)
+        assert rel(out, c["out"]) <= TOL, c["name"]
+        grads = torch.autograd.grad((out * c["gy"].cuda()).sum(), [x, st, m.weight, m.modulation.weight, m.modulation.bias])
+        for i, (a, b) in enumerate(zip(grads, c["grads"])):
+            assert rel(a, b) <= 3 * TOL, (c["name"], i)
+
+
+@pytest.mark.parametrize("cin,cout,res,up", [(64, 64, 16, False), (64, 32, 8, True), (128, 128, 12, False), (32, 64, 9, True)])
+def test_styled_conv_vs_oracle(cin, cout, res, up):
+    """StyledConv_without_noise (the IDEAS block) at tensor-core-eligible widths."""
+    from ideas_b200.stylegan2 import model as M
+    torch.manual_seed(12)
+    m = M.StyledConv_without_noise(cin, cout, 3, 48, upsample=up)
+    m.activate.bias.data.normal_()
+    x = torch.randn(2, cin, res, res)
+    st = torch.rand(2, 48) * 2 - 1
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "kernel" not in k) for k, v in m.state_dict().items()}
+    xr, sr = x.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    want = O.styled_conv(xr, sr, sd["conv.weight"], sd["conv.modulation.weight"], sd["conv.modulation.bias"],
+                         sd["activate.bias"], upsample=up, blur_kernel=sd.get("conv.blur.kernel"))
+    gy = torch.randn_like(want)
+    names = ["conv.weight", "conv.modulation.weight", "conv.modulation.bias", "activate.bias"]
+    wg = torch.autograd.grad(want, [xr, sr] + [sd[n] for n in names], gy)
+    m = m.cuda()
+    xc, sc = x.cuda().requires_grad_(True), st.cuda().requires_grad_(True)
+    got = m(xc, sc)
+    params = dict(m.named_parameters())
+    gg = torch.autograd.grad(got, [xc, sc] + [params[n] for n in names], gy.cuda())
+    assert rel(got, want) <= TOL
+    for i, (a, b) in enumerate(zip(gg, wg)):
+        assert rel(a, b) <= 3 * TOL, i
+
+
+def test_styled_conv_noise_and_torgb_golden(ops):
+    from ideas_b200.stylegan2 import model as M
+    c = ops["styledconv_noise"]
+    m = M.StyledConv(6, 10, 3, 12)
+    m.load_state_dict(c["sd"])
+    m = m.cuda()
+    assert rel(m(c["x"].cuda(), c["style"].cuda(), noise=c["noise"].cuda()), c["out"]) <= TOL
+    c = ops["torgb"]
+    t = M.ToRGB(6, 12, upsample=True)
+    t.load_state_dict(c["sd"])
+    t = t.cuda()
+    assert rel(t(c["x"].cuda(), c["style"].cuda(), c["skip"].cuda()), c["out"]) <= TOL

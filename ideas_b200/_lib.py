@@ -31,6 +31,7 @@ _P = c_void_p
 _PROTOTYPES = {
     "ideas_abi_version": [],
     "ideas_device_cc": [],
+    "ideas_umma_available": [],
     "ideas_fused_bias_act": [_P, _P, _P, _P, c_int, c_int, c_float, c_float, c_int64, c_int64, c_int, _P],
     "ideas_bias_act_backward": [_P, _P, _P, _P, c_float, c_float, c_int64, c_int64, c_int, _P],
     "ideas_modconv_act_backward": [_P, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_int64, c_int, _P],
@@ -121,7 +122,7 @@ def umma_enabled() -> bool:
     if os.environ.get("IDEAS_B200_UMMA", "1") == "0":
         return False
     L = lib()
-    return bool(getattr(L, "ideas_umma_available", None) and L.ideas_umma_available())
+    return bool(L.ideas_umma_available())
 
 
 def check(rc: int, what: str) -> None:

@@ -1,8 +1,580 @@
-// tcgen05 / TMA implicit-GEMM convolution (placeholder until the kernels land).
+// A1/A5: implicit-GEMM convolution on the Blackwell tensor path (tcgen05.mma kind::tf32,
+// TMEM accumulators, TMA-fed 128-byte-swizzled shared memory).  The reference has no native code
+// here: it calls cuDNN through F.conv2d / F.conv_transpose2d (stylegan2/model.py:115,258,267,273;
+// models.py:32).
+//
+// Forward-form kernel (forward conv, data gradient, transposed conv -- every ConvGeom):
+//   GEMM  D[pixel, k] = sum_{tap, c} X[pixel + tap, c] * Wp[tap][k][c]
+//   * no im2col buffer: for each (tap, 32-channel slab) ONE 4-D TMA box (32 ch x BW x BH x BN pixels,
+//     BW*BH*BN = 128) lands the shifted pixel patch in shared memory as 128 rows x 128 B -- exactly the
+//     K-major SWIZZLE_128B operand layout tcgen05 wants; zero padding is the TMA out-of-bounds fill.
+//     Stride-2 sources are addressed through per-parity tensor maps (no elementStrides).
+//   * CTA tile = 256 pixels (two 128-row sub-tiles, two accumulators) x BLOCK_N output channels, so
+//     each weight slab fetched from L2 feeds two MMAs (the kernel is L2->SM-feed bound: fp32 operands).
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread) + TMEM owner, warps 2-5 = epilogue:
+//     tcgen05.ld -> demodulation d[n,k] -> +bias -> leaky ReLU*gain -> 128-bit NHWC stores.
+// Weight-gradient kernel: see conv_umma_wgrad below.
 #include "common.cuh"
 #include "conv_geom.h"
+#include "umma_ptx.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
 namespace ideas {
-int umma_conv_launch(const ConvGeom&, float*, const float*, const float*, const float*, const float*, int, float, float,
-                     cudaStream_t, bool) { return IDEAS_ERR_UNSUPPORTED; }
-int umma_wgrad_launch(const ConvGeom&, float*, const float*, const float*, cudaStream_t, bool) { return IDEAS_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;   // pixels per sub-tile == UMMA M
+constexpr int kSub = 2;        // sub-tiles per CTA
+constexpr int kBlockK = 32;    // fp32 channels per k-block (= 128 B swizzle span)
+constexpr int kUmmaK = 8;      // tf32 K per instruction (32 B)
+constexpr uint32_t kABytes = kBlockM * 128;
+
+struct TapU {
+  int16_t oy, ox;   // offset added to the box origin (in units of the addressed map's pixels)
+  int16_t widx;     // weight tap index
+  int16_t map;      // which source tensor map (parity)
+};
+
+struct alignas(64) FwdParams {
+  CUtensorMap src[4];
+  CUtensorMap w;
+  float* dst;
+  const float* out_scale;
+  const float* bias;
+  int N, QH, QW;
+  int OH, OW, OC;
+  int o_s, o_py, o_px;
+  int bw, bh, bn;
+  int tiles_x, tiles_y, subtiles;
+  int ntaps, csteps;
+  int act;
+  float alpha, gain;
+  TapU taps[kMaxTaps];
+};
+
+template <int BN> struct FwdCfg {
+  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kStageBytes = kSub * kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 6 ? 6 : (200 * 1024 / kStageBytes);
+  static constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid_constant__ FwdParams p) {
+  using Cfg = FwdCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int k0 = blockIdx.x * BN;
+  const int nkb = p.ntaps * p.csteps;
+
+  // sub-tile origins
+  int qx0[kSub], qy0[kSub], n0[kSub];
+  bool sub_ok[kSub];
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) {
+    const int id = blockIdx.y * kSub + j;
+    sub_ok[j] = id < p.subtiles;
+    const int bx = id % p.tiles_x;
+    const int t = id / p.tiles_x;
+    qx0[j] = bx * p.bw;
+    qy0[j] = (t % p.tiles_y) * p.bh;
+    n0[j] = (t / p.tiles_y) * p.bn;
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), Cfg::kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      ptx::tma_prefetch_desc(&p.w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int t = kb / p.csteps;
+        const int c0 = (kb - t * p.csteps) * kBlockK;
+        const TapU tp = p.taps[t];
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+        ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+        const uint32_t sa = tiles + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < kSub; ++j)
+          ptx::tma_load_4d(sa + j * kABytes, &p.src[tp.map], fb, c0, qx0[j] + tp.ox, qy0[j] + tp.oy, n0[j]);
+        ptx::tma_load_3d(sa + kSub * kABytes, &p.w, fb, c0, k0, tp.widx);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = ptx::idesc_tf32(kBlockM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = tiles + stage * Cfg::kStageBytes;
+        const uint64_t bdesc = ptx::smem_desc_sw128(sa + kSub * kABytes, 16, 1024);
+#pragma unroll
+        for (int j = 0; j < kSub; ++j) {
+          const uint64_t adesc = ptx::smem_desc_sw128(sa + j * kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            ptx::mma_tf32(tmem_base + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+        }
+        ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));   // frees the stage when these MMAs retire
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::mma_commit(ptx::smem_u32(&accum_bar));
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < kSub; ++j) {
+      const int wq = row % p.bw;
+      const int t = row / p.bw;
+      const int qx = qx0[j] + wq, qy = qy0[j] + (t % p.bh), n = n0[j] + t / p.bh;
+      const bool valid = sub_ok[j] && n < p.N && qy < p.QH && qx < p.QW;
+      float* dp = nullptr;
+      const float* os = nullptr;
+      if (valid) {
+        dp = p.dst + (((int64_t)n * p.OH + (qy * p.o_s + p.o_py)) * p.OW + (qx * p.o_s + p.o_px)) * p.OC + k0;
+        if (p.out_scale) os = p.out_scale + (int64_t)n * p.OC + k0;
+      }
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + ch * 32), v);
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (os) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(os + ch * 32 + i));
+              r.x *= s.x; r.y *= s.y; r.z *= s.z; r.w *= s.w;
+            }
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + i));
+              r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+            }
+            if (p.act == IDEAS_ACT_LRELU) {
+              r.x = lrelu(r.x, p.alpha) * p.gain; r.y = lrelu(r.y, p.alpha) * p.gain;
+              r.z = lrelu(r.z, p.alpha) * p.gain; r.w = lrelu(r.w, p.alpha) * p.gain;
+            }
+            *reinterpret_cast<float4*>(dp + ch * 32 + i) = r;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+// fp32 tensor viewed as rank-`rank` (innermost first), 128-byte swizzle, zero OOB fill
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  auto enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return IDEAS_ERR_CUDA;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return IDEAS_ERR_CUDA;
+  }
+  return IDEAS_OK;
+}
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// choose the 128-pixel box (bw x bh x bn) that covers the q grid with the fewest sub-tiles
+void choose_box(int N, int QH, int QW, int* bw, int* bh, int* bn, int* tx, int* ty, int* subtiles) {
+  long best = -1;
+  for (int w = 16; w >= 4; w >>= 1) {
+    if (w > pow2_ceil(QW) && w > 4) continue;
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      if (h > pow2_ceil(QH) && h > 1) continue;
+      const int n = 128 / (w * h);
+      const long cnt = (long)ceil_div(QW, w) * ceil_div(QH, h) * ceil_div(N, n);
+      if (best < 0 || cnt < best) {
+        best = cnt; *bw = w; *bh = h; *bn = n; *tx = ceil_div(QW, w); *ty = ceil_div(QH, h);
+      }
+    }
+  }
+  *subtiles = (int)best;
+}
+
+template <int BN>
+int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
+  using Cfg = FwdCfg<BN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_umma_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma: cudaFuncSetAttribute");
+  dim3 grid(ntiles_n, ceil_div(p.subtiles, kSub));
+  conv_umma_fwd_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(p);
+  IDEAS_CHECK_LAUNCH("conv_umma_fwd");
+  return IDEAS_OK;
+}
+
+}  // namespace
+
+int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
+                     const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run) {
+  // ---- eligibility
+  if (g.IC % 32 || g.OC % 32 || g.ntaps < 1) return IDEAS_ERR_UNSUPPORTED;
+  if (g.i_s != 1 && g.i_s != 2) return IDEAS_ERR_UNSUPPORTED;
+  if ((int64_t)g.N * g.QH * g.QW < 256 || g.QW < 2) return IDEAS_ERR_UNSUPPORTED;   // tiny problems: SIMT
+  if (!aligned16(dst) || !aligned16(src) || !aligned16(w) || (out_scale && !aligned16(out_scale)) ||
+      (bias && !aligned16(bias)))
+    return IDEAS_ERR_UNSUPPORTED;
+  if (g.IH > 32767 || g.IW > 32767) return IDEAS_ERR_UNSUPPORTED;
+  if (dry_run) return IDEAS_OK;
+
+  FwdParams p;
+  p.dst = dst; p.out_scale = out_scale; p.bias = bias;
+  p.N = g.N; p.QH = g.QH; p.QW = g.QW; p.OH = g.OH; p.OW = g.OW; p.OC = g.OC;
+  p.o_s = g.o_s; p.o_py = g.o_py; p.o_px = g.o_px;
+  p.act = act; p.alpha = alpha; p.gain = gain;
+  p.ntaps = g.ntaps; p.csteps = g.IC / kBlockK;
+  choose_box(g.N, g.QH, g.QW, &p.bw, &p.bh, &p.bn, &p.tiles_x, &p.tiles_y, &p.subtiles);
+
+  // ---- taps -> (map, offset); which parity maps are needed
+  bool need[4] = {false, false, false, false};
+  int max_widx = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    const ConvTap& tp = g.taps[t];
+    int py = 0, px = 0, oy = tp.dy, ox = tp.dx;
+    if (g.i_s == 2) {
+      py = ((tp.dy % 2) + 2) % 2; px = ((tp.dx % 2) + 2) % 2;
+      oy = (tp.dy - py) / 2; ox = (tp.dx - px) / 2;
+    }
+    p.taps[t].oy = (int16_t)oy; p.taps[t].ox = (int16_t)ox; p.taps[t].widx = (int16_t)tp.widx;
+    p.taps[t].map = (int16_t)(py * 2 + px);
+    need[py * 2 + px] = true;
+    if (tp.widx > max_widx) max_widx = tp.widx;
+  }
+  const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  for (int m = 0; m < 4; ++m) {
+    if (!need[m]) continue;
+    const int py = m >> 1, px = m & 1;
+    const int s = g.i_s;
+    const int64_t wd = (g.IW - px + s - 1) / s, hd = (g.IH - py + s - 1) / s;
+    if (wd < 1 || hd < 1) return IDEAS_ERR_UNSUPPORTED;
+    const uint64_t dims[4] = {(uint64_t)g.IC, (uint64_t)wd, (uint64_t)hd, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)s * g.IC * 4, (uint64_t)s * g.IW * g.IC * 4, (uint64_t)g.IH * g.IW * g.IC * 4};
+    const float* base = src + ((int64_t)py * g.IW + px) * g.IC;
+    int rc = encode_map(&p.src[m], base, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int m = 0; m < 4; ++m)
+    if (!need[m]) p.src[m] = p.src[need[0] ? 0 : (need[1] ? 1 : (need[2] ? 2 : 3))];
+
+  const int BN = (g.OC % 256 == 0) ? 256 : (g.OC % 128 == 0) ? 128 : (g.OC % 64 == 0) ? 64 : 32;
+  {
+    const uint64_t dims[3] = {(uint64_t)g.IC, (uint64_t)g.OC, (uint64_t)(max_widx + 1)};
+    const uint64_t strides[2] = {(uint64_t)g.IC * 4, (uint64_t)g.OC * g.IC * 4};
+    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)BN, 1u};
+    int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
+    if (rc) return rc;
+  }
+  switch (BN) {
+    case 256: return launch_fwd<256>(p, g.OC / 256, st);
+    case 128: return launch_fwd<128>(p, g.OC / 128, st);
+    case 64: return launch_fwd<64>(p, g.OC / 64, st);
+    default: return launch_fwd<32>(p, g.OC / 32, st);
+  }
+}
+
+// ==========================================================================================
+// weight gradient:  dWp[tap][k][c] += sum_pixels dY[pixel, k] * X[pixel*stride + tap, c]
+//   GEMM per tap with M = 128 output channels, N = BNC input channels, reduction over pixels.
+//   Both operands are "MN-major": the reduction index (pixel) is the row of the NHWC tensors and the
+//   GEMM M/N index (channel) is contiguous.  One 5-D TMA box (32 ch x bw x bh x bn pixels x channel
+//   groups) per operand lands [channel group][32 pixels][32 ch] in shared memory, which is the
+//   MN-major SWIZZLE_128B canonical layout: LBO = stride between 32-channel groups (4 KB), SBO =
+//   stride between 8-pixel groups (1 KB); each tcgen05.mma consumes 8 pixels (K = 8 for tf32).
+//   grid = (k-tiles * c-tiles, taps, pixel splits); partial sums are merged with vector red.add.
+// ==========================================================================================
+namespace {
+
+constexpr int kWgPix = 32;                       // pixels per k-block
+constexpr uint32_t kWgABytes = 4 * kWgPix * 128; // 128 output channels
+
+struct alignas(64) WgradParams {
+  CUtensorMap dy;        // (32, OW, OH, N, OC/32)
+  CUtensorMap x[4];      // (32, Wd, Hd, N, IC/32) per parity
+  float* dwp;
+  int OC, IC;
+  int bw, bh, bn;        // pixel box, bw*bh*bn == 32
+  int tiles_x, tiles_y, nboxes;
+  int boxes_per_split;
+  int ctiles;
+  TapU taps[kMaxTaps];
+};
+
+template <int BNC> struct WgCfg {
+  static constexpr uint32_t kBBytes = (BNC / 32) * kWgPix * 128;
+  static constexpr uint32_t kStageBytes = kWgABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr uint32_t kTmemCols = BNC < 32 ? 32 : BNC;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BNC>
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgCfg<BNC>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int ktile = blockIdx.x / p.ctiles, ctile = blockIdx.x - ktile * p.ctiles;
+  const int k0 = ktile * 128, c0 = ctile * BNC;
+  const TapU tp = p.taps[blockIdx.y];
+  const int b_begin = blockIdx.z * p.boxes_per_split;
+  const int b_end = min(b_begin + p.boxes_per_split, p.nboxes);
+  const int nkb = b_end - b_begin;
+  if (nkb <= 0) return;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), Cfg::kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int id = b_begin + kb;
+        const int bx = id % p.tiles_x;
+        const int t = id / p.tiles_x;
+        const int qx0 = bx * p.bw, qy0 = (t % p.tiles_y) * p.bh, n0 = (t / p.tiles_y) * p.bn;
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+        ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+        const uint32_t sa = tiles + stage * Cfg::kStageBytes;
+        ptx::tma_load_5d(sa, &p.dy, fb, 0, qx0, qy0, n0, k0 / 32);
+        ptx::tma_load_5d(sa + kWgABytes, &p.x[tp.map], fb, 0, qx0 + tp.ox, qy0 + tp.oy, n0, c0 / 32);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_tf32(128, BNC, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = tiles + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int k = 0; k < kWgPix / kUmmaK; ++k) {
+          const uint64_t adesc = ptx::smem_desc_sw128(sa + k * 1024, kWgPix * 128, 1024);
+          const uint64_t bdesc = ptx::smem_desc_sw128(sa + kWgABytes + k * 1024, kWgPix * 128, 1024);
+          ptx::mma_tf32(tmem_base, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+        }
+        ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::mma_commit(ptx::smem_u32(&accum_bar));
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int k = k0 + quarter * 32 + lane;
+    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
+    ptx::tc_fence_after();
+    float* dp = p.dwp + ((int64_t)tp.widx * p.OC + k) * p.IC + c0;
+    for (int ch = 0; ch < BNC / 32; ++ch) {
+      float v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
+      if (k < p.OC && c0 + ch * 32 < p.IC) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) red_add_v4(dp + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+void choose_box32(int N, int QH, int QW, int* bw, int* bh, int* bn, int* tx, int* ty, int* nboxes) {
+  long best = -1;
+  for (int w = 32; w >= 1; w >>= 1) {
+    if (w > pow2_ceil(QW) && w > 1) continue;
+    for (int h = 32 / w; h >= 1; h >>= 1) {
+      if (h > pow2_ceil(QH) && h > 1) continue;
+      const int n = 32 / (w * h);
+      const long cnt = (long)ceil_div(QW, w) * ceil_div(QH, h) * ceil_div(N, n);
+      if (best < 0 || cnt < best) {
+        best = cnt; *bw = w; *bh = h; *bn = n; *tx = ceil_div(QW, w); *ty = ceil_div(QH, h);
+      }
+    }
+  }
+  *nboxes = (int)best;
+}
+
+template <int BNC>
+int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
+  using Cfg = WgCfg<BNC>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_umma_wgrad_kernel<BNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_wgrad: cudaFuncSetAttribute");
+  conv_umma_wgrad_kernel<BNC><<<grid, kThreads, Cfg::kSmemBytes, st>>>(p);
+  IDEAS_CHECK_LAUNCH("conv_umma_wgrad");
+  return IDEAS_OK;
+}
+
+}  // namespace
+
+// g is the FORWARD geometry (src = x, dst = dy); dwp is zero-initialised / accumulated into.
+int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float* dy, cudaStream_t st, bool dry_run) {
+  if (g.IC % 32 || g.OC % 32 || g.ntaps < 1 || g.o_s != 1) return IDEAS_ERR_UNSUPPORTED;
+  if (g.i_s != 1 && g.i_s != 2) return IDEAS_ERR_UNSUPPORTED;
+  if ((int64_t)g.N * g.QH * g.QW < 512) return IDEAS_ERR_UNSUPPORTED;
+  if (!aligned16(dwp) || !aligned16(x) || !aligned16(dy)) return IDEAS_ERR_UNSUPPORTED;
+  if (g.IH > 32767 || g.IW > 32767) return IDEAS_ERR_UNSUPPORTED;
+  if (dry_run) return IDEAS_OK;
+
+  WgradParams p;
+  p.dwp = dwp; p.OC = g.OC; p.IC = g.IC;
+  choose_box32(g.N, g.QH, g.QW, &p.bw, &p.bh, &p.bn, &p.tiles_x, &p.tiles_y, &p.nboxes);
+  const int BNC = g.IC >= 256 && g.IC % 256 == 0 ? 256 : (g.IC > 64 ? 128 : (g.IC > 32 ? 64 : 32));
+  p.ctiles = ceil_div(g.IC, BNC);
+  const int ktiles = ceil_div(g.OC, 128);
+
+  bool need[4] = {false, false, false, false};
+  for (int t = 0; t < g.ntaps; ++t) {
+    const ConvTap& tp = g.taps[t];
+    int py = 0, px = 0, oy = tp.dy, ox = tp.dx;
+    if (g.i_s == 2) {
+      py = ((tp.dy % 2) + 2) % 2; px = ((tp.dx % 2) + 2) % 2;
+      oy = (tp.dy - py) / 2; ox = (tp.dx - px) / 2;
+    }
+    p.taps[t].oy = (int16_t)oy; p.taps[t].ox = (int16_t)ox; p.taps[t].widx = (int16_t)tp.widx;
+    p.taps[t].map = (int16_t)(py * 2 + px);
+    need[py * 2 + px] = true;
+  }
+  {
+    const uint64_t dims[5] = {32, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N, (uint64_t)(g.OC / 32)};
+    const uint64_t strides[4] = {(uint64_t)g.OC * 4, (uint64_t)g.OW * g.OC * 4, (uint64_t)g.OH * g.OW * g.OC * 4, 128};
+    const uint32_t box[5] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 4};
+    int rc = encode_map(&p.dy, dy, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int m = 0; m < 4; ++m) {
+    if (!need[m]) continue;
+    const int py = m >> 1, px = m & 1, s = g.i_s;
+    const int64_t wd = (g.IW - px + s - 1) / s, hd = (g.IH - py + s - 1) / s;
+    if (wd < 1 || hd < 1) return IDEAS_ERR_UNSUPPORTED;
+    const uint64_t dims[5] = {32, (uint64_t)wd, (uint64_t)hd, (uint64_t)g.N, (uint64_t)(g.IC / 32)};
+    const uint64_t strides[4] = {(uint64_t)s * g.IC * 4, (uint64_t)s * g.IW * g.IC * 4, (uint64_t)g.IH * g.IW * g.IC * 4, 128};
+    const uint32_t box[5] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BNC / 32)};
+    int rc = encode_map(&p.x[m], x + ((int64_t)py * g.IW + px) * g.IC, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int m = 0; m < 4; ++m)
+    if (!need[m]) p.x[m] = p.x[need[0] ? 0 : (need[1] ? 1 : (need[2] ? 2 : 3))];
+
+  const int base = ktiles * p.ctiles * g.ntaps;
+  int splits = ceil_div(kNumSMs * 2, base);
+  if (splits > p.nboxes) splits = p.nboxes;
+  if (splits < 1) splits = 1;
+  p.boxes_per_split = ceil_div(p.nboxes, splits);
+  splits = ceil_div(p.nboxes, p.boxes_per_split);
+  dim3 grid(ktiles * p.ctiles, g.ntaps, splits);
+  switch (BNC) {
+    case 256: return launch_wgrad<256>(p, grid, st);
+    case 128: return launch_wgrad<128>(p, grid, st);
+    case 64: return launch_wgrad<64>(p, grid, st);
+    default: return launch_wgrad<32>(p, grid, st);
+  }
+}
+
 }  // namespace ideas
+
+extern "C" int ideas_umma_available(void) { return 1; }

@@ -21,8 +21,8 @@ from torch import nn
 from .stylegan2.model import (Blur, EqualConv2d, EqualLinear, ScaledLeakyReLU,
                               StyledConv_without_noise as StyledConv)
 from .stylegan2.op import FusedLeakyReLU
-from .stylegan2.op import conv2d as _ops
-from .stylegan2.op.conv2d import PackWeight
+from .stylegan2.op import conv as _ops
+from .stylegan2.op.conv import PackWeight
 from .stylegan2.op.elementwise import add_scale
 
 _INV_SQRT2 = 1.0 / math.sqrt(2.0)

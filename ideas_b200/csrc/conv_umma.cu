@@ -221,7 +221,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // fp32 tensor viewed as rank-`rank` (innermost first), 128-byte swizzle, zero OOB fill
 int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+               const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -232,7 +232,7 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", (int)r,
@@ -352,8 +352,10 @@ int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
 //   Both operands are "MN-major": the reduction index (pixel) is the row of the NHWC tensors and the
 //   GEMM M/N index (channel) is contiguous.  One 5-D TMA box (32 ch x bw x bh x bn pixels x channel
 //   groups) per operand lands [channel group][32 pixels][32 ch] in shared memory, which is the
-//   MN-major SWIZZLE_128B canonical layout: LBO = stride between 32-channel groups (4 KB), SBO =
-//   stride between 8-pixel groups (1 KB); each tcgen05.mma consumes 8 pixels (K = 8 for tf32).
+//   MN-major canonical layout.  For 32-bit MN-major operands tcgen05 accepts only the "128 B swizzle
+//   with 32 B atom" pattern (descriptor layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+//   LBO = stride between 32-channel groups (4 KB), SBO = stride between 4-pixel groups (512 B); each
+//   tcgen05.mma consumes 8 pixels (K = 8 for tf32).
 //   grid = (k-tiles * c-tiles, taps, pixel splits); partial sums are merged with vector red.add.
 // ==========================================================================================
 namespace {
@@ -447,8 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_wgrad_kernel(const __gr
         const uint32_t sa = tiles + stage * Cfg::kStageBytes;
 #pragma unroll
         for (int k = 0; k < kWgPix / kUmmaK; ++k) {
-          const uint64_t adesc = ptx::smem_desc_sw128(sa + k * 1024, kWgPix * 128, 1024);
-          const uint64_t bdesc = ptx::smem_desc_sw128(sa + kWgABytes + k * 1024, kWgPix * 128, 1024);
+          const uint64_t adesc = ptx::smem_desc_sw128_base32(sa + k * 1024, kWgPix * 128, 512);
+          const uint64_t bdesc = ptx::smem_desc_sw128_base32(sa + kWgABytes + k * 1024, kWgPix * 128, 512);
           ptx::mma_tf32(tmem_base, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
         }
         ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));
@@ -543,7 +545,7 @@ int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float
     const uint64_t dims[5] = {32, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N, (uint64_t)(g.OC / 32)};
     const uint64_t strides[4] = {(uint64_t)g.OC * 4, (uint64_t)g.OW * g.OC * 4, (uint64_t)g.OH * g.OW * g.OC * 4, 128};
     const uint32_t box[5] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, 4};
-    int rc = encode_map(&p.dy, dy, 5, dims, strides, box);
+    int rc = encode_map(&p.dy, dy, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   for (int m = 0; m < 4; ++m) {
@@ -554,7 +556,8 @@ int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float
     const uint64_t dims[5] = {32, (uint64_t)wd, (uint64_t)hd, (uint64_t)g.N, (uint64_t)(g.IC / 32)};
     const uint64_t strides[4] = {(uint64_t)s * g.IC * 4, (uint64_t)s * g.IW * g.IC * 4, (uint64_t)g.IH * g.IW * g.IC * 4, 128};
     const uint32_t box[5] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BNC / 32)};
-    int rc = encode_map(&p.x[m], x + ((int64_t)py * g.IW + px) * g.IC, 5, dims, strides, box);
+    int rc = encode_map(&p.x[m], x + ((int64_t)py * g.IW + px) * g.IC, 5, dims, strides, box,
+                        CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   for (int m = 0; m < 4; ++m)

@@ -107,9 +107,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (64 bit): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout [61,64) with 2 = 128-byte swizzle.
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+// K-major operands: 16-byte chunks swizzled within 128 B (TMA CU_TENSOR_MAP_SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(addr, lbo_bytes, sbo_bytes, 2u);
+}
+// MN-major 32-bit operands: the only legal layout is "128 B swizzle, 32 B atom" (layout type 1):
+// 32-byte chunks XOR-ed with (row mod 4); atom = 128 B x 4 rows.  TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t smem_desc_sw128_base32(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(addr, lbo_bytes, sbo_bytes, 1u);
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate: c_format=F32 [4,6), a/b_format=TF32 [7,10),[10,13),
 // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).

@@ -32,6 +32,7 @@ _PROTOTYPES = {
     "ideas_abi_version": [],
     "ideas_device_cc": [],
     "ideas_umma_available": [],
+    "ideas_set_option": [ctypes.c_char_p, c_int],
     "ideas_fused_bias_act": [_P, _P, _P, _P, c_int, c_int, c_float, c_float, c_int64, c_int64, c_int, _P],
     "ideas_bias_act_backward": [_P, _P, _P, _P, c_float, c_float, c_int64, c_int64, c_int, _P],
     "ideas_modconv_act_backward": [_P, _P, _P, _P, _P, _P, c_float, c_float, c_int, c_int64, c_int, _P],

@@ -58,6 +58,8 @@ const char* ideas_last_error(void);
 unsigned long long ideas_launch_count(void);
 /* 1 when the tcgen05/TMA convolution kernels are compiled into this build */
 int ideas_umma_available(void);
+/* tuning knobs; "tma_tf32" = 1: tensor maps use the TFLOAT32 data type (TMA converts on load) */
+int ideas_set_option(const char* name, int value);
 /* compute capability major*10+minor of the current device, or a negative error */
 int ideas_device_cc(void);
 

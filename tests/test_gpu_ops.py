@@ -10,6 +10,8 @@ import torch.nn.functional as F
 
 from oracle import functional as O
 
+import tolerances as T
+
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3          # north-star tolerance (tcgen05 / TF32 paths)
@@ -162,35 +164,28 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", ["simt", "auto"])
-def test_conv2d_fwd_dgrad_wgrad(case, impl):
-    from ideas_b200 import _lib
+def test_conv2d_fwd_dgrad_wgrad(case, conv_mode):
     from ideas_b200.stylegan2.op import conv as C
     N, Ci, K, H, W, k, stride, pad = case
     g = torch.Generator().manual_seed(9)
     x = torch.randn(N, Ci, H, W, generator=g)
     w = torch.randn(K, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5
     b = torch.randn(K, generator=g)
-    old = C.set_default_impl(_lib.IMPL_SIMT if impl == "simt" else _lib.IMPL_AUTO)
-    try:
-        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
-        want = O.fused_leaky_relu(F.conv2d(xr, wr, None, stride, pad), br)
-        gy = torch.randn(want.shape, generator=g)
-        wg = torch.autograd.grad(want, [xr, wr, br], gy)
-        xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
-        wp = C.PackWeight.apply(wc, False, 1.0)
-        got = C.conv2d(xc, wp, bc, K=K, kh=k, kw=k, stride=stride, pad=pad, act=True)
-        gg = torch.autograd.grad(got, [xc, wc, bc], gy.cuda())
-        tol = TOL_FP32 if impl == "simt" else TOL
-        assert rel(got, want) <= tol
-        for a, c in zip(gg, wg):
-            assert rel(a, c) <= tol * 3
-    finally:
-        C.set_default_impl(old)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    want = O.fused_leaky_relu(F.conv2d(xr, wr, None, stride, pad), br)
+    gy = torch.randn(want.shape, generator=g)
+    wg = torch.autograd.grad(want, [xr, wr, br], gy)
+    xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    wp = C.PackWeight.apply(wc, False, 1.0)
+    got = C.conv2d(xc, wp, bc, K=K, kh=k, kw=k, stride=stride, pad=pad, act=True)
+    gg = torch.autograd.grad(got, [xc, wc, bc], gy.cuda())
+    assert T.rel(got, want) <= T.OUT[conv_mode]
+    for name, a, c in zip(("dx", "dw", "db"), gg, wg):
+        T.assert_grad_through_act(a, c, conv_mode, name)
 
 
 @pytest.mark.parametrize("case", [(2, 16, 8, 7, 7, 1, 2), (2, 64, 32, 16, 16, 3, 2), (1, 32, 32, 5, 6, 3, 1), (2, 128, 64, 16, 16, 1, 2)])
-def test_conv_transpose2d(case):
+def test_conv_transpose2d(case, conv_mode):
     from ideas_b200.stylegan2.op import conv as C
     N, Ci, Co, H, W, k, stride = case
     g = torch.Generator().manual_seed(10)
@@ -204,12 +199,12 @@ def test_conv_transpose2d(case):
     wp = C.PackWeight.apply(wc, False, 1.0)
     got = C.conv_transpose2d(xc, wp, C_out=Co, kh=k, kw=k, stride=stride, pad=0)
     gg = torch.autograd.grad(got, [xc, wc], gy.cuda())
-    assert rel(got, want) <= TOL
+    assert T.rel(got, want) <= T.OUT[conv_mode]
     for a, c in zip(gg, wg):
-        assert rel(a, c) <= TOL * 3
+        assert T.rel(a, c) <= T.GRAD[conv_mode]
 
 
-def test_conv_second_order_r1_style():
+def test_conv_second_order_r1_style(conv_mode):
     """R1 differentiates dD/dx w.r.t. the weights: conv double-backward (utils.py:112-118)."""
     from ideas_b200.stylegan2.op import conv as C
     g = torch.Generator().manual_seed(11)
@@ -237,8 +232,8 @@ def test_conv_second_order_r1_style():
         pen = gx.pow(2).sum()
         return (pen,) + torch.autograd.grad(pen, [a, c])
 
-    for a, c in zip(ours(), oracle()):
-        assert rel(a, c) <= TOL
+    for name, a, c in zip(("penalty", "dw1", "dw2"), ours(), oracle()):
+        T.assert_grad_through_act(a, c, conv_mode, name)
 
 
 # ------------------------------------------------------------------ A1/A2 modulated convolution
@@ -252,20 +247,20 @@ def _load_modconv(c):
     return m.cuda()
 
 
-def test_modulated_conv_golden(ops):
+def test_modulated_conv_golden(ops, conv_mode):
     for c in ops["modconv"]:
         m = _load_modconv(c)
         x = c["x"].cuda().requires_grad_(True)
         st = c["style"].cuda().requires_grad_(True)
         out = m(x, st)
-        assert rel(out, c["out"]) <= TOL, c["name"]
+        assert T.rel(out, c["out"]) <= T.OUT[conv_mode], c["name"]
         grads = torch.autograd.grad((out * c["gy"].cuda()).sum(), [x, st, m.weight, m.modulation.weight, m.modulation.bias])
         for i, (a, b) in enumerate(zip(grads, c["grads"])):
-            assert rel(a, b) <= 3 * TOL, (c["name"], i)
+            assert T.rel(a, b) <= T.GRAD[conv_mode], (c["name"], i)
 
 
 @pytest.mark.parametrize("cin,cout,res,up", [(64, 64, 16, False), (64, 32, 8, True), (128, 128, 12, False), (32, 64, 9, True)])
-def test_styled_conv_vs_oracle(cin, cout, res, up):
+def test_styled_conv_vs_oracle(cin, cout, res, up, conv_mode):
     """StyledConv_without_noise (the IDEAS block) at tensor-core-eligible widths."""
     from ideas_b200.stylegan2 import model as M
     torch.manual_seed(12)
@@ -285,12 +280,12 @@ def test_styled_conv_vs_oracle(cin, cout, res, up):
     got = m(xc, sc)
     params = dict(m.named_parameters())
     gg = torch.autograd.grad(got, [xc, sc] + [params[n] for n in names], gy.cuda())
-    assert rel(got, want) <= TOL
-    for i, (a, b) in enumerate(zip(gg, wg)):
-        assert rel(a, b) <= 3 * TOL, i
+    assert T.rel(got, want) <= T.OUT[conv_mode]
+    for name, a, b in zip(["dx", "dstyle"] + names, gg, wg):
+        T.assert_grad_through_act(a, b, conv_mode, name)
 
 
-def test_styled_conv_noise_and_torgb_golden(ops):
+def test_styled_conv_noise_and_torgb_golden(ops, conv_mode):
     from ideas_b200.stylegan2 import model as M
     c = ops["styledconv_noise"]
     m = M.StyledConv(6, 10, 3, 12)

@@ -16,7 +16,7 @@ from ctypes import c_float, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libideas_b200.so")
-SOURCES = ["bias_act.cu", "upfirdn2d.cu", "conv_simt.cu", "conv_umma.cu", "elementwise.cu", "bits.cu"]
+SOURCES = ["bias_act.cu", "upfirdn2d.cu", "conv_simt.cu", "conv_umma.cu", "conv_pointwise.cu", "elementwise.cu", "bits.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -46,6 +46,8 @@ _PROTOTYPES = {
     "ideas_scale_channels": [_P, _P, _P, c_int, c_int64, c_int, _P],
     "ideas_channel_dot": [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P],
     "ideas_add_scale": [_P, _P, _P, c_float, c_int64, _P],
+    "ideas_patchify_forward": [_P, _P, _P] + [c_int] * 7 + [_P],
+    "ideas_patchify_backward": [_P, _P, _P] + [c_int] * 7 + [_P],
     "ideas_bits_encode": [_P, _P, _P, c_int, c_int, c_int, c_float, _P],
     "ideas_bits_decode": [_P, _P, c_int, c_int, c_int, _P],
     "ideas_bits_count_errors": [_P, _P, _P, c_int64, _P],

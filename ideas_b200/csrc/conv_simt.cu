@@ -19,6 +19,10 @@ namespace ideas {
 int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
                      const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run);
 int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* src, const float* dy, cudaStream_t st, bool dry_run);
+// implemented in conv_pointwise.cu: 1x1 convs with <= 4 channels on one side (HBM-bound streaming kernels)
+int pointwise_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* bias, int act,
+                          float alpha, float gain, cudaStream_t st);
+int pointwise_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float* dy, cudaStream_t st);
 
 struct ConvArgs {
   ConvGeom g;
@@ -412,6 +416,10 @@ extern "C" int ideas_conv2d_forward(float* y, const float* x, const float* wp, c
   IDEAS_REQUIRE(y && x && wp, "conv2d_forward: null pointer");
   const ConvGeom g = geom_forward(N, H, W, C, K, kh, kw, stride, pad, OH, OW);
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl == IDEAS_IMPL_AUTO && !in_scale && !out_scale) {
+    rc = pointwise_conv_launch(g, y, x, wp, bias, act, alpha, gain, st);
+    if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
+  }
   if (umma_wanted(impl) && !in_scale) {
     rc = umma_conv_launch(g, y, x, wp, out_scale, bias, act, alpha, gain, st, false);
     if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
@@ -439,8 +447,10 @@ extern "C" int ideas_conv2d_dgrad(float* dx, const float* dy, const float* wpt, 
       if (py >= H || px >= W) continue;
       const ConvGeom g = geom_dgrad_phase(N, H, W, C, K, kh, kw, stride, pad, OH, OW, py, px);
       rc = IDEAS_ERR_UNSUPPORTED;
+      if (impl == IDEAS_IMPL_AUTO && !in_scale && !out_scale)
+        rc = pointwise_conv_launch(g, dx, dy, wpt, bias, act, alpha, gain, st);
       // in this geometry the GEMM reduces over K: `out_scale` (per dy channel) plays the input role
-      if (umma_wanted(impl) && !out_scale)
+      if (rc == IDEAS_ERR_UNSUPPORTED && umma_wanted(impl) && !out_scale)
         rc = umma_conv_launch(g, dx, dy, wpt, in_scale, bias, act, alpha, gain, st, false);
       if (rc == IDEAS_ERR_UNSUPPORTED) {
         if (impl == IDEAS_IMPL_UMMA) {
@@ -464,6 +474,10 @@ extern "C" int ideas_conv2d_wgrad(float* dwp, const float* x, const float* dy, c
   IDEAS_REQUIRE(dwp && x && dy, "conv2d_wgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const ConvGeom g = geom_forward(N, H, W, C, K, kh, kw, stride, pad, OH, OW);
+  if (impl == IDEAS_IMPL_AUTO && !in_scale && !out_scale) {
+    rc = pointwise_wgrad_launch(g, dwp, x, dy, st);
+    if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
+  }
   if (umma_wanted(impl) && !in_scale && !out_scale) {
     rc = umma_wgrad_launch(g, dwp, x, dy, st, false);
     if (rc != IDEAS_ERR_UNSUPPORTED) return rc;

@@ -182,3 +182,116 @@ extern "C" int ideas_add_scale(float* out, const float* a, const float* b, float
   IDEAS_CHECK_LAUNCH("add_scale");
   return IDEAS_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// patchify: the reference cuts n_crop random boxes out of every image and
+// bilinearly resizes each to (th, tw) with a Python loop of F.interpolate calls (utils.py:127-149).
+// Here the boxes are DATA (int32 (n_crop, 4) = y, x, h, w on the device, shared by the whole batch as in
+// the reference), so one launch serves any crop geometry -- which also makes the step CUDA-graph safe.
+// Sampling follows F.interpolate(mode="bilinear", align_corners=False): src = (dst + 0.5) * (h / th) - 0.5,
+// clamped at 0, neighbours clamped at the crop edge.  NHWC, one thread per output pixel.
+// ---------------------------------------------------------------------------------------
+namespace ideas {
+
+struct BilinearTap { int i0, i1; float l0, l1; };
+
+__device__ __forceinline__ BilinearTap bilinear_tap(int dst, int in_size, int out_size) {
+  const float scale = (float)in_size / (float)out_size;
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  BilinearTap t;
+  t.i0 = (int)src;
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  t.l1 = src - (float)t.i0;
+  t.l0 = 1.f - t.l1;
+  return t;
+}
+
+__global__ void __launch_bounds__(256) patchify_fwd_kernel(float* __restrict__ out, const float* __restrict__ img,
+                                                           const int* __restrict__ boxes, int B, int H, int W, int C,
+                                                           int n_crop, int th, int tw) {
+  const int64_t total = (int64_t)B * n_crop * th * tw;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int tx = (int)(idx % tw);
+    int64_t t = idx / tw;
+    const int ty = (int)(t % th);
+    t /= th;
+    const int j = (int)(t % n_crop);
+    const int b = (int)(t / n_crop);
+    const int y0 = __ldg(boxes + j * 4), x0 = __ldg(boxes + j * 4 + 1), h = __ldg(boxes + j * 4 + 2), w = __ldg(boxes + j * 4 + 3);
+    const BilinearTap ty_ = bilinear_tap(ty, h, th), tx_ = bilinear_tap(tx, w, tw);
+    const float* base = img + (int64_t)b * H * W * C;
+    const float* p00 = base + ((int64_t)(y0 + ty_.i0) * W + (x0 + tx_.i0)) * C;
+    const float* p01 = base + ((int64_t)(y0 + ty_.i0) * W + (x0 + tx_.i1)) * C;
+    const float* p10 = base + ((int64_t)(y0 + ty_.i1) * W + (x0 + tx_.i0)) * C;
+    const float* p11 = base + ((int64_t)(y0 + ty_.i1) * W + (x0 + tx_.i1)) * C;
+    float* o = out + idx * C;
+    for (int c = 0; c < C; ++c)
+      o[c] = ty_.l0 * (tx_.l0 * __ldg(p00 + c) + tx_.l1 * __ldg(p01 + c)) +
+             ty_.l1 * (tx_.l0 * __ldg(p10 + c) + tx_.l1 * __ldg(p11 + c));
+  }
+}
+
+__global__ void __launch_bounds__(256) patchify_bwd_kernel(float* __restrict__ gimg, const float* __restrict__ gout,
+                                                           const int* __restrict__ boxes, int B, int H, int W, int C,
+                                                           int n_crop, int th, int tw) {
+  const int64_t total = (int64_t)B * n_crop * th * tw;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int tx = (int)(idx % tw);
+    int64_t t = idx / tw;
+    const int ty = (int)(t % th);
+    t /= th;
+    const int j = (int)(t % n_crop);
+    const int b = (int)(t / n_crop);
+    const int y0 = __ldg(boxes + j * 4), x0 = __ldg(boxes + j * 4 + 1), h = __ldg(boxes + j * 4 + 2), w = __ldg(boxes + j * 4 + 3);
+    const BilinearTap ty_ = bilinear_tap(ty, h, th), tx_ = bilinear_tap(tx, w, tw);
+    float* base = gimg + (int64_t)b * H * W * C;
+    float* p00 = base + ((int64_t)(y0 + ty_.i0) * W + (x0 + tx_.i0)) * C;
+    float* p01 = base + ((int64_t)(y0 + ty_.i0) * W + (x0 + tx_.i1)) * C;
+    float* p10 = base + ((int64_t)(y0 + ty_.i1) * W + (x0 + tx_.i0)) * C;
+    float* p11 = base + ((int64_t)(y0 + ty_.i1) * W + (x0 + tx_.i1)) * C;
+    const float* g = gout + idx * C;
+    for (int c = 0; c < C; ++c) {
+      const float v = g[c];
+      atomicAdd(p00 + c, ty_.l0 * tx_.l0 * v);
+      atomicAdd(p01 + c, ty_.l0 * tx_.l1 * v);
+      atomicAdd(p10 + c, ty_.l1 * tx_.l0 * v);
+      atomicAdd(p11 + c, ty_.l1 * tx_.l1 * v);
+    }
+  }
+}
+
+}  // namespace ideas
+
+static int check_patchify(const char* who, int B, int H, int W, int C, int n_crop, int th, int tw) {
+  IDEAS_REQUIRE(B >= 0 && H >= 1 && W >= 1 && C >= 1 && n_crop >= 0 && th >= 1 && tw >= 1, "%s: bad shape", who);
+  return IDEAS_OK;
+}
+
+extern "C" int ideas_patchify_forward(float* out, const float* img, const int* boxes, int B, int H, int W, int C,
+                                      int n_crop, int th, int tw, void* stream) {
+  int rc = check_patchify("patchify_forward", B, H, W, C, n_crop, th, tw);
+  if (rc) return rc;
+  const int64_t total = (int64_t)B * n_crop * th * tw;
+  if (total == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(out && img && boxes, "patchify_forward: null pointer");
+  int64_t blocks = ideas::ceil_div64(total, 256);
+  if (blocks > ideas::kNumSMs * 8) blocks = ideas::kNumSMs * 8;
+  ideas::patchify_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, img, boxes, B, H, W, C, n_crop, th, tw);
+  IDEAS_CHECK_LAUNCH("patchify_forward");
+  return IDEAS_OK;
+}
+
+extern "C" int ideas_patchify_backward(float* gimg, const float* gout, const int* boxes, int B, int H, int W, int C,
+                                       int n_crop, int th, int tw, void* stream) {
+  int rc = check_patchify("patchify_backward", B, H, W, C, n_crop, th, tw);
+  if (rc) return rc;
+  const int64_t total = (int64_t)B * n_crop * th * tw;
+  if (total == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(gimg && gout && boxes, "patchify_backward: null pointer");
+  int64_t blocks = ideas::ceil_div64(total, 256);
+  if (blocks > ideas::kNumSMs * 8) blocks = ideas::kNumSMs * 8;
+  ideas::patchify_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(gimg, gout, boxes, B, H, W, C, n_crop, th, tw);
+  IDEAS_CHECK_LAUNCH("patchify_backward");
+  return IDEAS_OK;
+}

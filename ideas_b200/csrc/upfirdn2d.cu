@@ -71,7 +71,10 @@ __device__ __forceinline__ float4 fma4(const float4& a, float s, const float4& a
 }
 __device__ __forceinline__ float4 mul4(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
-template <int ROWS, bool EPI>
+// XT adjacent output columns per thread: a row of XT+3 input vectors feeds XT outputs, so the
+// L1/LSU traffic per output drops from 4 loads to (XT+3)/XT (the kernel is L1-wavefront bound
+// otherwise: at HBM rate 4 loads + 1 store per element would need ~115 B/clk/SM of the 128 available).
+template <int ROWS, int XT, bool EPI>
 __global__ void __launch_bounds__(256) blur4_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x,
                                                          const float* __restrict__ kernel,
                                                          const float* __restrict__ bias, UpfirdnParams p) {
@@ -83,60 +86,66 @@ __global__ void __launch_bounds__(256) blur4_nhwc_kernel(float* __restrict__ out
     for (int kx = 0; kx < 4; ++kx)
       tp.k[ky][kx] = (ky < p.kh && kx < p.kw) ? __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)) : 0.f;
   const int c4n = p.minor >> 2;
-  const int lin = blockIdx.x * blockDim.x + threadIdx.x;  // (ox, c4), c4 fastest
-  if (lin >= p.out_w * c4n) return;
-  const int ox = lin / c4n;
-  const int c = (lin - ox * c4n) << 2;
+  const int groups = (p.out_w + XT - 1) / XT;
+  const int lin = blockIdx.x * blockDim.x + threadIdx.x;  // (column group, c4), c4 fastest
+  if (lin >= groups * c4n) return;
+  const int og = lin / c4n;
+  const int c = (lin - og * c4n) << 2;
+  const int ox0 = og * XT;
   const int m = blockIdx.z;
   const int oy0 = blockIdx.y * ROWS;
   const int oy1 = min(oy0 + ROWS, p.out_h);
-  const int ix0 = ox - p.pad_x0;
+  const int ix0 = ox0 - p.pad_x0;
 
   const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
-  float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox) * p.minor + c;
+  float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
   const int64_t orow = (int64_t)p.out_w * p.minor;
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (EPI) b4 = *reinterpret_cast<const float4*>(bias + c);
 
-  bool colok[4];
+  bool colok[XT + 3];
 #pragma unroll
-  for (int kx = 0; kx < 4; ++kx) colok[kx] = (ix0 + kx) >= 0 && (ix0 + kx) < p.in_w;
+  for (int i = 0; i < XT + 3; ++i) colok[i] = (ix0 + i) >= 0 && (ix0 + i) < p.in_w;
 
-  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s0[XT], s1[XT], s2[XT];
+#pragma unroll
+  for (int j = 0; j < XT; ++j) s0[j] = s1[j] = s2[j] = zero;
   // input rows oy0-pad .. oy1-1-pad+3 ; output row (iy + pad - 3) completes at input row iy
   const int iy_begin = oy0 - p.pad_y0;
   const int iy_end = oy1 - 1 - p.pad_y0 + 3;
   for (int iy = iy_begin; iy <= iy_end; ++iy) {
-    float4 r[4];
+    float4 r[XT + 3];
     const bool rowok = iy >= 0 && iy < p.in_h;
     const float* rp = xin + ((int64_t)iy * p.in_w + ix0) * p.minor;
 #pragma unroll
-    for (int kx = 0; kx < 4; ++kx) {
-      r[kx] = (rowok && colok[kx]) ? __ldg(reinterpret_cast<const float4*>(rp + (int64_t)kx * p.minor))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float4 h[4];
-#pragma unroll
-    for (int ky = 0; ky < 4; ++ky) {
-      float4 a = mul4(r[0], tp.k[ky][0]);
-      a = fma4(r[1], tp.k[ky][1], a);
-      a = fma4(r[2], tp.k[ky][2], a);
-      a = fma4(r[3], tp.k[ky][3], a);
-      h[ky] = a;
-    }
-    float4 done = make_float4(s2.x + h[3].x, s2.y + h[3].y, s2.z + h[3].z, s2.w + h[3].w);
-    s2 = make_float4(s1.x + h[2].x, s1.y + h[2].y, s1.z + h[2].z, s1.w + h[2].w);
-    s1 = make_float4(s0.x + h[1].x, s0.y + h[1].y, s0.z + h[1].z, s0.w + h[1].w);
-    s0 = h[0];
+    for (int i = 0; i < XT + 3; ++i)
+      r[i] = (rowok && colok[i]) ? __ldg(reinterpret_cast<const float4*>(rp + (int64_t)i * p.minor)) : zero;
     const int oy = iy + p.pad_y0 - 3;
-    if (oy >= oy0) {
-      if (EPI) {
-        done.x = lrelu(done.x + b4.x, p.alpha) * p.gain;
-        done.y = lrelu(done.y + b4.y, p.alpha) * p.gain;
-        done.z = lrelu(done.z + b4.z, p.alpha) * p.gain;
-        done.w = lrelu(done.w + b4.w, p.alpha) * p.gain;
+#pragma unroll
+    for (int j = 0; j < XT; ++j) {
+      float4 h[4];
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        float4 a = mul4(r[j], tp.k[ky][0]);
+        a = fma4(r[j + 1], tp.k[ky][1], a);
+        a = fma4(r[j + 2], tp.k[ky][2], a);
+        a = fma4(r[j + 3], tp.k[ky][3], a);
+        h[ky] = a;
       }
-      st_stream4(o + (int64_t)oy * orow, done);
+      float4 done = make_float4(s2[j].x + h[3].x, s2[j].y + h[3].y, s2[j].z + h[3].z, s2[j].w + h[3].w);
+      s2[j] = make_float4(s1[j].x + h[2].x, s1[j].y + h[2].y, s1[j].z + h[2].z, s1[j].w + h[2].w);
+      s1[j] = make_float4(s0[j].x + h[1].x, s0[j].y + h[1].y, s0[j].z + h[1].z, s0[j].w + h[1].w);
+      s0[j] = h[0];
+      if (oy >= oy0 && ox0 + j < p.out_w) {
+        if (EPI) {
+          done.x = lrelu(done.x + b4.x, p.alpha) * p.gain;
+          done.y = lrelu(done.y + b4.y, p.alpha) * p.gain;
+          done.z = lrelu(done.z + b4.z, p.alpha) * p.gain;
+          done.w = lrelu(done.w + b4.w, p.alpha) * p.gain;
+        }
+        st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, done);
+      }
     }
   }
 }
@@ -172,10 +181,10 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
                     minor % 4 == 0 && aligned16(out) && aligned16(x) && (!bias || aligned16(bias)) && major <= 65535;
   if (fast) {
     const int c4n = minor / 4;
-    constexpr int ROWS = 32;
-    dim3 grid(ceil_div(p.out_w * c4n, 256), ceil_div(p.out_h, ROWS), major);
-    if (bias) blur4_nhwc_kernel<ROWS, true><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
-    else blur4_nhwc_kernel<ROWS, false><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
+    constexpr int ROWS = 32, XT = 4;
+    dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 256), ceil_div(p.out_h, ROWS), major);
+    if (bias) blur4_nhwc_kernel<ROWS, XT, true><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
+    else blur4_nhwc_kernel<ROWS, XT, false><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
     IDEAS_CHECK_LAUNCH("upfirdn2d(fast)");
     return IDEAS_OK;
   }

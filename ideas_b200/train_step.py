@@ -21,6 +21,7 @@ import torch.distributed as dist
 from torch import optim
 from torch.nn import functional as F
 
+from . import _lib
 from .models import init_model
 from .utils import (accumulate, d_logistic_loss, d_r1_loss, draw_crops, g_nonsaturating_loss, patchify_image,
                     requires_grad)
@@ -76,9 +77,16 @@ class Trainer:
     """The ``trainer`` dict of train.py:390-432 as an object (``trainer[key]`` still works)."""
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
-                 states: Optional[Dict[str, dict]] = None):
+                 states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False):
         self.args = args
         self.device = torch.device(device)
+        self.cuda_graphs = bool(cuda_graphs and self.device.type == "cuda")
+        self._graphs: Dict[tuple, tuple] = {}
+        self.replayed_launches = 0        # library kernels launched through graph replays (see bench.py gpu_launches)
+        self._pool = None
+        self._static_X: Optional[torch.Tensor] = None
+        self._static_boxes: Optional[Dict[str, torch.Tensor]] = None
+        self._host_boxes: Optional[Dict[str, torch.Tensor]] = None
         if seed is not None:
             torch.manual_seed(seed)
         self.nets: Dict[str, torch.nn.Module] = {}
@@ -96,10 +104,11 @@ class Trainer:
             accumulate(self.nets[key + "_ema"], self.nets[key], 0)
         P = lambda *ks: [p for k in ks for p in self.nets[k].parameters()]  # noqa: E731
         fused = bool(fused_adam and self.device.type == "cuda")
-        self.g_optim = optim.Adam(P("E", "G", "Gstru"), lr=args.lr, betas=(0.0, 0.99), fused=fused)
-        self.ex_optim = optim.Adam(P("Ex"), lr=args.lr, betas=(0.0, 0.99), fused=fused)
+        kw = dict(fused=fused, capturable=self.cuda_graphs)
+        self.g_optim = optim.Adam(P("E", "G", "Gstru"), lr=args.lr, betas=(0.0, 0.99), **kw)
+        self.ex_optim = optim.Adam(P("Ex"), lr=args.lr, betas=(0.0, 0.99), **kw)
         r = args.d_reg_every / (args.d_reg_every + 1)
-        self.d_optim = optim.Adam(P("Dreal", "Dco", "Ddist"), lr=args.lr * r, betas=(0.0 ** r, 0.99 ** r), fused=fused)
+        self.d_optim = optim.Adam(P("Dreal", "Dco", "Ddist"), lr=args.lr * r, betas=(0.0 ** r, 0.99 ** r), **kw)
         self.reducers = {}
         for name, opt in (("g", self.g_optim), ("ex", self.ex_optim), ("d", self.d_optim)):
             red = FlatGradAllReduce([p for grp in opt.param_groups for p in grp["params"]])
@@ -129,23 +138,96 @@ class Trainer:
                 off += p.numel()
 
     # -------------------------------------------------------------------------------------
-    def _rand_like_Z(self, S, draws, key):
+    def _rand_like_Z(self, S, draws, key, device_rng=False):
         if draws is not None and key in draws:
             return draws[key].to(self.device)
+        shape = (S.shape[0], self.args.N, S.shape[2], S.shape[3])
+        if device_rng:                     # CUDA-graph path: Philox on the device (no H2D copy inside the graph)
+            return torch.rand(shape, dtype=torch.float, device=self.device) * 2 - 1
         # train.py:60-61 draws on the CPU generator and copies; kept so seeded runs match the reference
-        return torch.rand(size=(S.shape[0], self.args.N, S.shape[2], S.shape[3]), dtype=torch.float).to(self.device) * 2 - 1
+        return torch.rand(size=shape, dtype=torch.float).to(self.device) * 2 - 1
 
     def _rand_like_T(self, T, draws, key):
         if draws is not None and key in draws:
             return draws[key].to(self.device)
         return torch.rand_like(T) * 2 - 1
 
+    # box sets one iteration needs: name -> number of crops (train.py:80-82,168-169)
+    def _box_specs(self):
+        a = self.args
+        return {"fake_crops_d": a.n_crop, "real_crops_d": a.n_crop, "ref_crops_d": a.ref_crop * a.n_crop,
+                "fake_crops_g": a.n_crop, "ref_crops_g": a.ref_crop * a.n_crop}
+
     def step(self, X: torch.Tensor, iter_idx: int, draws: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """One iteration on batch X (already on the device).  Returns the loss tensors (device
-        scalars; ``.item()`` them only when logging, as train.py:224-232 does)."""
+        scalars; ``.item()`` them only when logging, as train.py:224-232 does).  With
+        ``cuda_graphs=True`` (and no explicit ``draws``) the whole iteration is replayed as one CUDA
+        graph per variant (with / without lazy R1, container switch)."""
+        a = self.args
+        r1 = iter_idx % a.d_reg_every == 0
+        late = iter_idx > a.num_iters * 0.8
+        if self.cuda_graphs and draws is None:
+            return self._step_graphed(X, r1, late)
+        return self._step_eager(X, r1, late, draws)
+
+    # ------------------------------------------------------------------------------------- CUDA graphs
+    def _refresh_boxes(self, H, W):
+        """Draw this iteration's crop boxes like the reference (CPU RNG) and stage them into the static
+        device tensors the captured patchify kernels read."""
+        for key, n in self._box_specs().items():
+            self._host_boxes[key].copy_(torch.tensor(draw_crops(n, H, W), dtype=torch.int32))
+            self._static_boxes[key].copy_(self._host_boxes[key], non_blocking=True)
+
+    def _step_graphed(self, X, r1, late):
+        H, W = X.shape[2], X.shape[3]
+        if self._static_X is None:
+            self._static_X = torch.empty_like(X)
+            self._static_boxes = {k: torch.zeros((n, 4), dtype=torch.int32, device=self.device)
+                                  for k, n in self._box_specs().items()}
+            self._host_boxes = {k: torch.zeros((n, 4), dtype=torch.int32).pin_memory() for k, n in self._box_specs().items()}
+            self._static_X.copy_(X)
+            self._refresh_boxes(H, W)
+            # warm-up outside capture (lazy initialisation: Adam state, cuBLAS workspaces, kernel attributes,
+            # the flat all-reduce buckets): two eager iterations of the R1 variant, which covers every code path
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._step_eager(self._static_X, True, late, None, boxes=self._static_boxes, device_rng=True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            for opt in (self.g_optim, self.ex_optim, self.d_optim):
+                opt.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
+            self._pool = torch.cuda.graph_pool_handle()
+        key = (bool(r1), bool(late))
+        if key not in self._graphs:
+            self._static_X.copy_(X)
+            for opt in (self.g_optim, self.ex_optim, self.d_optim):
+                opt.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph, pool=self._pool):
+                losses = self._step_eager(self._static_X, r1, late, None, boxes=self._static_boxes, device_rng=True)
+                losses = {k: v.detach() for k, v in losses.items()}
+            self._graphs[key] = (graph, losses, _lib.launch_count() - n0)
+        graph, losses, n_kernels = self._graphs[key]
+        self._static_X.copy_(X, non_blocking=True)
+        self._refresh_boxes(H, W)
+        graph.replay()
+        self.replayed_launches += n_kernels
+        return losses
+
+    # ------------------------------------------------------------------------------------- eager core
+    def _step_eager(self, X, r1, late, draws, boxes=None, device_rng=False) -> Dict[str, torch.Tensor]:
         a, t = self.args, self.nets
         H, W = X.shape[2], X.shape[3]
-        crops = (lambda key, n: draws[key] if (draws is not None and key in draws) else draw_crops(n, H, W))
+
+        def crops(key, n):
+            if boxes is not None:
+                return boxes[key]
+            return draws[key] if (draws is not None and key in draws) else draw_crops(n, H, W)
+
         loss = {}
         # ---------------- discriminators (train.py:48-102)
         for k in EMA_KEYS:
@@ -153,7 +235,7 @@ class Trainer:
         for k in ("Dreal", "Dco", "Ddist"):
             requires_grad(t[k], True)
         S1, T1 = t["E"](X)
-        Z = self._rand_like_Z(S1, draws, "Z_d")
+        Z = self._rand_like_Z(S1, draws, "Z_d", device_rng)
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_d")
         hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
@@ -172,7 +254,7 @@ class Trainer:
         (D_real_loss + D_texture_loss + D_dist_loss).backward()
         self.d_optim.step()
         # ---------------- lazy R1 (train.py:105-129)
-        if iter_idx % a.d_reg_every == 0:
+        if r1:
             Xr = X.detach().requires_grad_(True)
             r1_real = d_r1_loss(t["Dreal"](Xr), Xr)
             rp = real_patch.detach().requires_grad_(True)
@@ -193,7 +275,7 @@ class Trainer:
         for k in ("Dreal", "Dco", "Ddist"):
             requires_grad(t[k], False)
         S1, T1 = t["E"](X)
-        Z = self._rand_like_Z(S1, draws, "Z_g")
+        Z = self._rand_like_Z(S1, draws, "Z_g", device_rng)
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_g")
         hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
@@ -204,7 +286,7 @@ class Trainer:
         ref_patch = patchify_image(X, a.ref_crop * a.n_crop, crops=crops("ref_crops_g", a.ref_crop * a.n_crop))
         fake_patch_pred, _ = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
         G_texture_loss = g_nonsaturating_loss(fake_patch_pred)
-        container = hat_X3 if iter_idx > a.num_iters * 0.8 else hat_X2
+        container = hat_X3 if late else hat_X2
         hat_S2, _ = t["E"](container)
         E_stru_loss = F.l1_loss(hat_S2, S2)
         Ex_loss = F.l1_loss(t["Ex"](hat_S2), Z)

@@ -19,6 +19,25 @@ from . import _lib
 from ._tensor import ptr, stream_ptr
 
 
+def time_change(seconds):
+    """Elapsed-time formatter of the training log ("2h 3m 4s" / "3m 4s" / "4s"; reference utils.py:12-34:
+    above one hour the seconds are shown after the minutes, at most two units otherwise)."""
+    seconds = float(seconds)
+    if seconds / 3600 > 1:
+        h = int(seconds / 3600)
+        m = int((seconds - h * 3600) / 60)
+        return f"{h}h {m}m {int(seconds - h * 3600 - m * 60)}s"
+    if seconds / 60 > 1:
+        m = int(seconds / 60)
+        return f"{m}m {int(seconds - m * 60)}s"
+    return f"{int(seconds)}s"
+
+
+def data_sampler(dataset, shuffle):
+    from torch.utils import data
+    return data.RandomSampler(dataset) if shuffle else data.SequentialSampler(dataset)
+
+
 def requires_grad(model, flag=True):
     for p in model.parameters():
         p.requires_grad = flag
@@ -67,16 +86,53 @@ def draw_crops(n_crop, height, width, min_size=1 / 8, max_size=1 / 4):
     return [(random.randrange(0, height - h), random.randrange(0, width - w), h, w) for h, w in zip(hs, ws)]
 
 
+class _Patchify(autograd.Function):
+    """(B,C,H,W) image, device int32 boxes (n_crop,4)=(y,x,h,w) -> (B*n_crop, C, th, tw), one kernel."""
+
+    @staticmethod
+    def forward(ctx, img, boxes, th, tw):
+        from ._tensor import empty_nhwc, nhwc, require_cuda
+        require_cuda(img)
+        img = nhwc(img)
+        b, c, h, w = img.shape
+        n_crop = boxes.shape[0]
+        out = empty_nhwc(b * n_crop, c, th, tw, img)
+        _lib.call("ideas_patchify_forward", ptr(out), ptr(img), ptr(boxes), b, h, w, c, n_crop, th, tw, stream_ptr(img))
+        ctx.save_for_backward(boxes)
+        ctx.cfg = (b, c, h, w, n_crop, th, tw)
+        return out
+
+    @staticmethod
+    @autograd.function.once_differentiable
+    def backward(ctx, g):
+        from ._tensor import nhwc
+        (boxes,) = ctx.saved_tensors
+        b, c, h, w, n_crop, th, tw = ctx.cfg
+        g = nhwc(g)
+        gimg = torch.zeros((b, h, w, c), device=g.device, dtype=g.dtype).permute(0, 3, 1, 2)
+        _lib.call("ideas_patchify_backward", ptr(gimg), ptr(g), ptr(boxes), b, h, w, c, n_crop, th, tw, stream_ptr(g))
+        return gimg, None, None, None
+
+
+def crops_to_device(crops, device):
+    """[(y, x, h, w)] -> int32 (n_crop, 4) device tensor (one small async copy from pinned memory)."""
+    host = torch.tensor(crops, dtype=torch.int32).reshape(-1, 4)
+    if torch.device(device).type == "cuda":
+        host = host.pin_memory()
+    return host.to(device, non_blocking=True)
+
+
 def patchify_image(img, n_crop, min_size=1 / 8, max_size=1 / 4, crops=None):
     """n_crop random crops per image, each resized (bilinear) to (H*max_size, W*max_size);
-    returns (B*n_crop, C, th, tw), crops of one image adjacent."""
+    returns (B*n_crop, C, th, tw), crops of one image adjacent (reference utils.py:127-149).
+    ``crops``: None (drawn like the reference), a list of (y, x, h, w), or a device int32 (n_crop, 4)
+    tensor.  One kernel launch whatever the crop sizes (the reference loops over F.interpolate)."""
     batch, channel, height, width = img.shape
     th, tw = int(height * max_size), int(width * max_size)
     if crops is None:
         crops = draw_crops(n_crop, height, width, min_size, max_size)
-    patches = [F.interpolate(img[:, :, y:y + h, x:x + w], size=(th, tw), mode="bilinear", align_corners=False)
-               for (y, x, h, w) in crops]
-    return torch.stack(patches, 1).reshape(-1, channel, th, tw)
+    boxes = crops if torch.is_tensor(crops) else crops_to_device(crops, img.device)
+    return _Patchify.apply(img, boxes, th, tw)
 
 
 # ---- bit path (reference utils.py:74-97, train.py:254-286)

@@ -173,6 +173,17 @@ int ideas_channel_dot(float* dot, float* out, const float* a, const float* b, co
 int ideas_add_scale(float* out, const float* a, const float* b, float gain, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * A10 / SURVEY §8(f)-1  patchify: n_crop boxes (device int32 (n_crop,4) = y,x,h,w, shared by the batch)
+ * cut from every NHWC image and resized to (th,tw) with F.interpolate(bilinear, align_corners=False)
+ * semantics -- replaces the Python loop of utils.py:127-149.  out (B*n_crop, th, tw, C), crops of one
+ * image adjacent.  The backward scatters with fp32 atomics into the zero-initialised `gimg`.
+ * ---------------------------------------------------------------------------------- */
+int ideas_patchify_forward(float* out, const float* img, const int* boxes, int B, int H, int W, int C,
+                           int n_crop, int th, int tw, void* stream);
+int ideas_patchify_backward(float* gimg, const float* gout, const int* boxes, int B, int H, int W, int C,
+                            int n_crop, int th, int tw, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * A9  bit path as integer kernels        restates utils.py:74-97, train.py:285
  * ---------------------------------------------------------------------------------- */
 /* z[b,l] = step*(n+0.5) - 1 + (u*r*2 - r), n = the sigma bits of group l, MSB first.

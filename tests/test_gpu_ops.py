@@ -160,6 +160,9 @@ CONV_CASES = [
     (2, 3, 32, 16, 16, 1, 1, 0), (2, 32, 64, 18, 18, 3, 1, 0), (2, 64, 64, 17, 17, 3, 2, 0), (1, 8, 128, 16, 16, 3, 1, 1),
     (2, 33, 7, 9, 11, 3, 1, 1), (2, 64, 32, 15, 15, 1, 2, 0), (3, 96, 48, 2, 2, 2, 1, 0), (2, 128, 3, 8, 8, 1, 1, 0),
     (1, 128, 128, 33, 33, 3, 2, 0), (2, 256, 512, 8, 8, 3, 1, 1),
+    # 1x1 convs with <= 4 channels on one side: the HBM-bound pointwise kernels (image ends of the nets)
+    (2, 3, 64, 64, 64, 1, 1, 0), (2, 128, 3, 32, 32, 1, 1, 0), (3, 1, 32, 16, 16, 1, 1, 0), (2, 32, 1, 16, 16, 1, 1, 0),
+    (2, 4, 256, 9, 7, 1, 1, 0), (1, 2048, 2, 5, 5, 1, 1, 0),
 ]
 
 
@@ -297,3 +300,30 @@ def test_styled_conv_noise_and_torgb_golden(ops, conv_mode):
     t.load_state_dict(c["sd"])
     t = t.cuda()
     assert rel(t(c["x"].cuda(), c["style"].cuda(), c["skip"].cuda()), c["out"]) <= TOL
+
+
+# ------------------------------------------------------------------ A10 patchify (utils.py:127-149)
+@pytest.mark.parametrize("B,C,H,W,n_crop", [(2, 3, 256, 256, 8), (3, 3, 64, 96, 5), (1, 4, 128, 128, 32)])
+def test_patchify_matches_interpolate_loop(B, C, H, W, n_crop):
+    import random
+    from ideas_b200 import utils as U
+    from oracle.train_step import draw_crops, patchify_image as oracle_patchify
+    torch.manual_seed(3)
+    random.seed(3)
+    crops = draw_crops(n_crop, H, W)
+    crops[0] = (0, 0, H // 4, W // 4)                       # identity-size crop: exact copy
+    crops[-1] = (H - H // 8, W - W // 8, H // 8, W // 8)    # smallest crop in the far corner (2x upsampling)
+    img = torch.rand(B, C, H, W) * 2 - 1
+    ir = img.clone().requires_grad_(True)
+    want = oracle_patchify(ir, crops)
+    gy = torch.randn_like(want)
+    (wg,) = torch.autograd.grad(want, ir, gy)
+    ic = img.cuda().requires_grad_(True)
+    got = U.patchify_image(ic, n_crop, crops=crops)
+    (gg,) = torch.autograd.grad(got, ic, gy.cuda())
+    assert got.shape == want.shape
+    assert rel(got, want) <= 2e-6
+    assert rel(gg, wg) <= 1e-5
+    # device-resident boxes give the same result (CUDA-graph path)
+    got2 = U.patchify_image(ic, n_crop, crops=U.crops_to_device(crops, "cuda"))
+    assert torch.equal(got2, got)

@@ -85,6 +85,18 @@ __global__ void __launch_bounds__(256) blur4_nhwc_kernel(float* __restrict__ out
 #pragma unroll
     for (int kx = 0; kx < 4; ++kx)
       tp.k[ky][kx] = (ky < p.kh && kx < p.kw) ? __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)) : 0.f;
+  // separable? (exact test: the binomial taps are small integers / 2^k, so rank 1 holds bit-exactly)
+  bool sep = tp.k[0][0] != 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) sep = sep && (tp.k[ky][kx] * tp.k[0][0] == tp.k[ky][0] * tp.k[0][kx]);
+  float kx[4], kyv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    kx[i] = tp.k[0][i];
+    kyv[i] = sep ? tp.k[i][0] / tp.k[0][0] : 0.f;
+  }
   const int c4n = p.minor >> 2;
   const int groups = (p.out_w + XT - 1) / XT;
   const int lin = blockIdx.x * blockDim.x + threadIdx.x;  // (column group, c4), c4 fastest
@@ -125,13 +137,23 @@ __global__ void __launch_bounds__(256) blur4_nhwc_kernel(float* __restrict__ out
 #pragma unroll
     for (int j = 0; j < XT; ++j) {
       float4 h[4];
+      if (sep) {
+        // rank-1 kernel (every IDEAS blur: outer([1,3,3,1])): one horizontal pass, scaled per kernel row
+        float4 a = mul4(r[j], kx[0]);
+        a = fma4(r[j + 1], kx[1], a);
+        a = fma4(r[j + 2], kx[2], a);
+        a = fma4(r[j + 3], kx[3], a);
 #pragma unroll
-      for (int ky = 0; ky < 4; ++ky) {
-        float4 a = mul4(r[j], tp.k[ky][0]);
-        a = fma4(r[j + 1], tp.k[ky][1], a);
-        a = fma4(r[j + 2], tp.k[ky][2], a);
-        a = fma4(r[j + 3], tp.k[ky][3], a);
-        h[ky] = a;
+        for (int ky = 0; ky < 4; ++ky) h[ky] = mul4(a, kyv[ky]);
+      } else {
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          float4 a = mul4(r[j], tp.k[ky][0]);
+          a = fma4(r[j + 1], tp.k[ky][1], a);
+          a = fma4(r[j + 2], tp.k[ky][2], a);
+          a = fma4(r[j + 3], tp.k[ky][3], a);
+          h[ky] = a;
+        }
       }
       float4 done = make_float4(s2[j].x + h[3].x, s2[j].y + h[3].y, s2[j].z + h[3].z, s2[j].w + h[3].w);
       s2[j] = make_float4(s1[j].x + h[2].x, s1[j].y + h[2].y, s1[j].z + h[2].z, s1[j].w + h[2].w);

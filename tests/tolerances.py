@@ -45,7 +45,7 @@ def assert_grad_through_act(a, b, mode, what=""):
         assert rel(a, b) <= GRAD["fp32"], (what, rel(a, b))
     elif a.numel() < 10000:
         # small reductions over all pixels (style, bias, per-sample scale gradients): every flip lands in them
-        assert rel(a, b) <= 2e-2, (what, "max", rel(a, b))
+        assert rel_l2(a, b) <= 5e-2, (what, "l2", rel_l2(a, b))
     else:
         assert rel_q(a, b) <= GRAD["tf32"], (what, "q95", rel_q(a, b))
         assert rel_l2(a, b) <= 5e-2, (what, "l2", rel_l2(a, b))

@@ -23,6 +23,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 namespace ideas {
@@ -286,6 +287,322 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   return IDEAS_OK;
 }
 
+
+// ==========================================================================================
+// Halo-reuse kernel (source stride 1, several taps): the implicit GEMM above fetches every shifted
+// 128-pixel patch again for each filter tap -- 9x the activation bytes of a 3x3 filter through L2,
+// and L2->SM bandwidth (~6300 B/clk chip-wide) is what bounds it.  Here the roles are swapped:
+//   D[k, pixel] = sum_{tap, c} Wp[tap][k][c] * X[pixel + tap, c]        (M = 128 output channels,
+//                                                                        N = pixels of the tile)
+// and ONE halo'd activation slab per 32-channel step -- a TMA box of (bh*pb + halo_y) image rows x
+// (bw + halo_x) columns, rows of 128 B in K-major SWIZZLE_128B -- serves every tap: the B descriptor
+// of tap (dy,dx) simply starts (dy*bwp + dx) rows further (tcgen05 computes the swizzle from the
+// address bits, so a start address that is not 1024-byte aligned is legal with base_offset 0;
+// scripts/probe_umma_offset.cu is the measurement).  The N extent therefore runs over the padded
+// row width bwp: the halo_x columns of every row produce outputs that are dropped, (bw/bwp of the
+// MMA work is useful), in exchange for ~9x fewer activation bytes.  Each CTA owns 128 output
+// channels x pb pixel blocks (pb*N <= 512 TMEM columns), so a 16 KB weight tile feeds pb MMAs.
+//   warp 0: weight-tile TMA producer (ring of kHaloWStages x 16 KB)
+//   warp 1: MMA issuer + TMEM owner
+//   warp 2 lane 0: activation-slab TMA producer (2 slots), then epilogue with warps 2..9
+//   epilogue: tcgen05.ld (lane = output channel, column = pixel) -> d[n,k] -> +bias -> lrelu*gain ->
+//             NHWC stores (a warp writes 32 consecutive channels of one pixel: 128 B)
+// ==========================================================================================
+constexpr int kHaloWStages = 4;
+constexpr int kHaloThreads = 320;            // warps 0/1 producers + MMA, warps 2..9 epilogue
+constexpr uint32_t kHaloWBytes = 128 * 128;   // 128 output channels x 32 fp32 input channels
+constexpr int kHaloSlack = 24;                // rows past the box that rounding N up to 16 may touch
+constexpr uint32_t kHaloMaxSlot = 80 * 1024;
+
+std::atomic<int> g_halo_mode{1};              // 0 = never, 1 = heuristic, 2 = whenever eligible
+
+struct TapH {
+  int32_t rowoff;   // (dy - min_dy) * bwp + (dx - min_dx)
+  int32_t widx;
+};
+
+struct alignas(64) HaloParams {
+  CUtensorMap src;
+  CUtensorMap w;
+  float* dst;
+  const float* out_scale;
+  const float* bias;
+  int N, QH, QW;
+  int OH, OW, OC;
+  int o_s, o_py, o_px;
+  int bw, bwp, bh, pb;
+  int nmma, box_rows;
+  int x_org, y_org;
+  int tiles_x, tiles_y;
+  int ntaps, csteps;
+  uint32_t x_slot_bytes, x_tx_bytes, tmem_cols;
+  int act;
+  float alpha, gain;
+  TapH taps[kMaxTaps];
+};
+
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const __grid_constant__ HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t wfull[kHaloWStages];
+  __shared__ __align__(8) uint64_t wempty[kHaloWStages];
+  __shared__ __align__(8) uint64_t xfull[2];
+  __shared__ __align__(8) uint64_t xempty[2];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t wring = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t xring = wring + kHaloWStages * kHaloWBytes;
+  const int k0 = blockIdx.x * 128;
+  const int bx = blockIdx.y % p.tiles_x;
+  const int tt = blockIdx.y / p.tiles_x;
+  const int qx0 = bx * p.bw;
+  const int qy0 = (tt % p.tiles_y) * (p.pb * p.bh);
+  const int n = tt / p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kHaloWStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&wfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&wempty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&xfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&xempty[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), p.tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== weight tiles: one (tap, 32-channel step) per ring slot =====
+      ptx::tma_prefetch_desc(&p.w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int cs = 0; cs < p.csteps; ++cs)
+        for (int t = 0; t < p.ntaps; ++t) {
+          ptx::mbar_wait(ptx::smem_u32(&wempty[stage]), phase ^ 1u);
+          const uint32_t fb = ptx::smem_u32(&wfull[stage]);
+          ptx::mbar_arrive_expect_tx(fb, kHaloWBytes);
+          ptx::tma_load_3d(wring + stage * kHaloWBytes, &p.w, fb, cs * kBlockK, k0, p.taps[t].widx);
+          if (++stage == kHaloWStages) { stage = 0; phase ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ptx::idesc_tf32(128, p.nmma, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int cs = 0; cs < p.csteps; ++cs) {
+        const int xs = cs & 1;
+        ptx::mbar_wait(ptx::smem_u32(&xfull[xs]), (uint32_t)(cs >> 1) & 1u);
+        const uint32_t xa = xring + xs * p.x_slot_bytes;
+        for (int t = 0; t < p.ntaps; ++t) {
+          ptx::mbar_wait(ptx::smem_u32(&wfull[stage]), phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::smem_desc_sw128(wring + stage * kHaloWBytes, 16, 1024);
+          for (int j = 0; j < p.pb; ++j) {
+            const uint64_t bdesc = ptx::smem_desc_sw128(xa + (uint32_t)(j * p.bh * p.bwp + p.taps[t].rowoff) * 128u, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              ptx::mma_tf32(tmem_base + j * p.nmma, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cs | t | k) != 0));
+          }
+          ptx::mma_commit(ptx::smem_u32(&wempty[stage]));
+          if (++stage == kHaloWStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(ptx::smem_u32(&xempty[xs]));   // the slab is free once every tap has consumed it
+      }
+      ptx::mma_commit(ptx::smem_u32(&accum_bar));
+    }
+  } else {
+    if (warp == 2 && lane == 0) {
+      // ===== activation slabs: one halo'd box per 32-channel step, double buffered =====
+      ptx::tma_prefetch_desc(&p.src);
+      for (int cs = 0; cs < p.csteps; ++cs) {
+        const int xs = cs & 1;
+        ptx::mbar_wait(ptx::smem_u32(&xempty[xs]), ((uint32_t)(cs >> 1) & 1u) ^ 1u);
+        const uint32_t fb = ptx::smem_u32(&xfull[xs]);
+        ptx::mbar_arrive_expect_tx(fb, p.x_tx_bytes);
+        ptx::tma_load_4d(xring + xs * p.x_slot_bytes, &p.src, fb, cs * kBlockK, qx0 + p.x_org, qy0 + p.y_org, n);
+      }
+    }
+    __syncwarp();
+    // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4 (lane = output channel); the two warps of a
+    // quarter take alternate 16-column chunks.  Within a chunk the 16 pixels span at most two tile rows
+    // (bwp >= 16), so every address is an independent function of the chunk origin: no serial chain. =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int k = k0 + quarter * 32 + lane;
+    const bool kok = k < p.OC;
+    float os = 1.f, bs = 0.f;
+    if (kok) {
+      if (p.out_scale) os = __ldg(p.out_scale + (int64_t)n * p.OC + k);
+      if (p.bias) bs = __ldg(p.bias + k);
+    }
+    const int npix = p.bh * p.bwp;
+    const int chunks_per_blk = (npix + 15) >> 4;
+    const int total_chunks = p.pb * chunks_per_blk;
+    const int xlim = min(p.bw, p.QW - qx0);
+    const int pix_step = p.o_s * p.OC;
+    const int row_step = p.o_s * p.OW * p.OC;
+    const bool lrelu_on = p.act == IDEAS_ACT_LRELU;
+    const float alpha = p.alpha, gain = lrelu_on ? p.gain : 1.f;
+    float* base = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + k;
+    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
+    ptx::tc_fence_after();
+    for (int c = half; c < total_chunks; c += 2) {
+      const int j = c / chunks_per_blk;
+      const int m0 = (c - j * chunks_per_blk) << 4;
+      const int y0 = m0 / p.bwp;
+      const int x0 = m0 - y0 * p.bwp;
+      const int ylim = min(p.bh, p.QH - qy0 - j * p.bh);   // rows of this pixel block inside the image
+      float v[16];
+      ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * p.nmma + m0), v);
+      float* r0 = base + (int64_t)(j * p.bh + y0) * row_step;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int xi = x0 + i;
+        const int wrap = xi >= p.bwp ? 1 : 0;
+        xi -= wrap ? p.bwp : 0;
+        const bool ok = kok && xi < xlim && (y0 + wrap) < ylim;
+        float r = fmaf(v[i], os, bs);
+        r = (lrelu_on && r < 0.f) ? r * alpha : r;
+        r *= gain;
+        if (ok) r0[wrap * row_step + xi * pix_step] = r;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+struct HaloTile {
+  int bw, bwp, bh, pb, nmma, tiles_x, tiles_y;
+  uint32_t slot_bytes;
+  double cycles;   // modelled cycles per 32-channel step over the whole q grid (one image)
+};
+
+// Pick (bw, bh, pb) minimising modelled time = tiles * max(MMA cycles, L2-feed cycles) per channel step.
+bool choose_halo_tile(int QW, int QH, int hx, int hy, int ntaps, HaloTile* out) {
+  struct Key { int a, b, c, d, e; bool operator<(const Key& o) const { return memcmp(this, &o, sizeof(Key)) < 0; } };
+  static std::mutex mu;
+  static std::map<Key, HaloTile> cache;
+  const Key key{QW, QH, hx, hy, ntaps};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return it->second.bw > 0; }
+  }
+  HaloTile best{};
+  best.bw = 0; best.cycles = 1e300;
+  for (int pb = 1; pb <= 2; ++pb)
+    for (int bw = 4; bw <= QW && bw + hx <= 256; ++bw) {
+      const int bwp = bw + hx;
+      if (bwp < 16) continue;   // the epilogue assumes a 16-pixel chunk spans at most two rows
+      for (int bh = 1; bh * bwp <= 256 && (bh - 1) * pb < QH; ++bh) {
+        const int nmma = ((bh * bwp + 15) / 16) * 16;
+        const int rows = pb * bh + hy;
+        if (rows > 256) break;
+        const uint32_t slot = (uint32_t)((rows * bwp + hx + kHaloSlack) * 128 + 1023) & ~1023u;
+        if (slot > kHaloMaxSlot) break;
+        const int tx = ceil_div(QW, bw), ty = ceil_div(QH, pb * bh);
+        const double mma = (double)ntaps * pb * 4 * (nmma / 2.0);
+        const double l2 = ((double)ntaps * kHaloWBytes + (double)rows * bwp * 128) / 42.0;
+        const double cyc = (double)tx * ty * (mma > l2 ? mma : l2) + (double)tx * ty * 40.0;   // + fixed cost per CTA
+        if (cyc < best.cycles) {
+          best.bw = bw; best.bwp = bwp; best.bh = bh; best.pb = pb; best.nmma = nmma; best.tiles_x = tx; best.tiles_y = ty;
+          best.slot_bytes = slot; best.cycles = cyc;
+        }
+      }
+    }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = best;
+  }
+  *out = best;
+  return best.bw > 0;
+}
+
+int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
+                     const float* bias, int act, float alpha, float gain, cudaStream_t st) {
+  const int mode = g_halo_mode.load();
+  if (mode == 0 || g.i_s != 1 || g.ntaps < 2) return IDEAS_ERR_UNSUPPORTED;
+  if (g.QW < 8 || g.QH < 1) return IDEAS_ERR_UNSUPPORTED;
+  int min_dx = 1 << 30, max_dx = -(1 << 30), min_dy = 1 << 30, max_dy = -(1 << 30), max_widx = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    min_dx = g.taps[t].dx < min_dx ? g.taps[t].dx : min_dx; max_dx = g.taps[t].dx > max_dx ? g.taps[t].dx : max_dx;
+    min_dy = g.taps[t].dy < min_dy ? g.taps[t].dy : min_dy; max_dy = g.taps[t].dy > max_dy ? g.taps[t].dy : max_dy;
+    max_widx = g.taps[t].widx > max_widx ? g.taps[t].widx : max_widx;
+  }
+  const int hx = max_dx - min_dx, hy = max_dy - min_dy;
+  if (hx > 8 || hy > 8) return IDEAS_ERR_UNSUPPORTED;
+  HaloTile tile;
+  if (!choose_halo_tile(g.QW, g.QH, hx, hy, g.ntaps, &tile)) return IDEAS_ERR_UNSUPPORTED;
+  if (mode == 1) {
+    // heuristic (scripts/kernels_microbench.py, IDEAS_HALO=0 vs 2): without an overlapped epilogue the halo
+    // kernel only wins where the pixel-major kernel's 128-pixel boxes straddle images (<= 16x16 maps)
+    if (g.OC < 128 || (g.OC % 128 != 0 && g.OC < 384) || g.QW > 16) return IDEAS_ERR_UNSUPPORTED;
+  }
+
+  HaloParams p;
+  p.dst = dst; p.out_scale = out_scale; p.bias = bias;
+  p.N = g.N; p.QH = g.QH; p.QW = g.QW; p.OH = g.OH; p.OW = g.OW; p.OC = g.OC;
+  p.o_s = g.o_s; p.o_py = g.o_py; p.o_px = g.o_px;
+  p.bw = tile.bw; p.bwp = tile.bwp; p.bh = tile.bh; p.pb = tile.pb; p.nmma = tile.nmma;
+  p.box_rows = tile.pb * tile.bh + hy;
+  p.x_org = min_dx; p.y_org = min_dy;
+  p.tiles_x = tile.tiles_x; p.tiles_y = tile.tiles_y;
+  p.ntaps = g.ntaps; p.csteps = g.IC / kBlockK;
+  p.x_slot_bytes = tile.slot_bytes;
+  p.x_tx_bytes = (uint32_t)(p.box_rows * p.bwp * 128);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.pb * p.nmma)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.act = act; p.alpha = alpha; p.gain = gain;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.taps[t].rowoff = (g.taps[t].dy - min_dy) * p.bwp + (g.taps[t].dx - min_dx);
+    p.taps[t].widx = g.taps[t].widx;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)g.IC, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)g.IC * 4, (uint64_t)g.IW * g.IC * 4, (uint64_t)g.IH * g.IW * g.IC * 4};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bwp, (uint32_t)p.box_rows, 1u};
+    int rc = encode_map(&p.src, src, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)g.IC, (uint64_t)g.OC, (uint64_t)(max_widx + 1)};
+    const uint64_t strides[2] = {(uint64_t)g.IC * 4, (uint64_t)g.OC * g.IC * 4};
+    const uint32_t wbox[3] = {(uint32_t)kBlockK, 128u, 1u};
+    int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
+    if (rc) return rc;
+  }
+  const uint32_t smem = kHaloWStages * kHaloWBytes + 2 * p.x_slot_bytes + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kHaloWStages * kHaloWBytes + 2 * kHaloMaxSlot + 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_halo: cudaFuncSetAttribute");
+  const int64_t ytiles = (int64_t)g.N * p.tiles_y * p.tiles_x;
+  if (ytiles > 65535) return IDEAS_ERR_UNSUPPORTED;
+  dim3 grid(ceil_div(g.OC, 128), (unsigned)ytiles);
+  conv_umma_halo_kernel<<<grid, kHaloThreads, smem, st>>>(p);
+  IDEAS_CHECK_LAUNCH("conv_umma_halo");
+  return IDEAS_OK;
+}
+
 }  // namespace
 
 int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
@@ -299,6 +616,10 @@ int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
     return IDEAS_ERR_UNSUPPORTED;
   if (g.IH > 32767 || g.IW > 32767) return IDEAS_ERR_UNSUPPORTED;
   if (dry_run) return IDEAS_OK;
+  {
+    const int rc = halo_conv_launch(g, dst, src, w, out_scale, bias, act, alpha, gain, st);
+    if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
+  }
 
   FwdParams p;
   p.dst = dst; p.out_scale = out_scale; p.bias = bias;
@@ -594,6 +915,10 @@ extern "C" int ideas_umma_available(void) { return 1; }
 extern "C" int ideas_set_option(const char* name, int value) {
   if (name && !strcmp(name, "tma_tf32")) {
     ideas::g_tma_tf32.store(value ? 1 : 0);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "halo")) {
+    ideas::g_halo_mode.store(value);
     return IDEAS_OK;
   }
   ideas::set_error("ideas_set_option: unknown option '%s'", name ? name : "(null)");

@@ -74,29 +74,14 @@ __device__ __forceinline__ float4 mul4(const float4& a, float s) { return make_f
 // XT adjacent output columns per thread: a row of XT+3 input vectors feeds XT outputs, so the
 // L1/LSU traffic per output drops from 4 loads to (XT+3)/XT (the kernel is L1-wavefront bound
 // otherwise: at HBM rate 4 loads + 1 store per element would need ~115 B/clk/SM of the 128 available).
+// general (non-separable) 4x4 taps: every input row is folded into three pending output rows
 template <int ROWS, int XT, bool EPI>
-__global__ void __launch_bounds__(256) blur4_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x,
-                                                         const float* __restrict__ kernel,
-                                                         const float* __restrict__ bias, UpfirdnParams p) {
-  // taps: flipped (true convolution) and zero-extended to 4x4; 16 uniform loads per thread
-  Taps4 tp;
-#pragma unroll
-  for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 4; ++kx)
-      tp.k[ky][kx] = (ky < p.kh && kx < p.kw) ? __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)) : 0.f;
-  // separable? (exact test: the binomial taps are small integers / 2^k, so rank 1 holds bit-exactly)
-  bool sep = tp.k[0][0] != 0.f;
-#pragma unroll
-  for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 4; ++kx) sep = sep && (tp.k[ky][kx] * tp.k[0][0] == tp.k[ky][0] * tp.k[0][kx]);
+__device__ __forceinline__ void blur4_general(float* __restrict__ out, const float* __restrict__ x,
+                                              const float* __restrict__ bias, const UpfirdnParams& p, const Taps4& tp) {
+  const bool sep = false;
   float kx[4], kyv[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    kx[i] = tp.k[0][i];
-    kyv[i] = sep ? tp.k[i][0] / tp.k[0][0] : 0.f;
-  }
+  for (int i = 0; i < 4; ++i) kx[i] = kyv[i] = 0.f;
   const int c4n = p.minor >> 2;
   const int groups = (p.out_w + XT - 1) / XT;
   const int lin = blockIdx.x * blockDim.x + threadIdx.x;  // (column group, c4), c4 fastest
@@ -172,6 +157,151 @@ __global__ void __launch_bounds__(256) blur4_nhwc_kernel(float* __restrict__ out
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// separable fast path (every blur IDEAS runs: outer([1,3,3,1]) * gain).  Same thread mapping as
+// above, but written for instruction count -- at HBM rate the kernel above is issue-bound (ncu:
+// 67 % issue-active, profiles/prof_blur_r1.raw.csv):
+//   * packed fp32x2 FMAs (fma.rn.f32x2): a float4 of channels is two instructions per tap;
+//   * the vertical pass is a 4-row sliding window of horizontal results kept in registers
+//     (slot rotation by a x4-unrolled row loop, no moves): 4 + 4 packed taps per output instead
+//     of scattering every row into three pending sums;
+//   * tiles that do not touch a border (all but the outer ring) skip every predicate.
+// ---------------------------------------------------------------------------------------
+struct f2x2 { unsigned long long lo, hi; };   // four channels as two packed fp32 pairs
+
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2x2 ldg_f2x2(const float* p) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  return f2x2{pack2(v.x, v.y), pack2(v.z, v.w)};
+}
+
+template <int XT, bool EPI, bool INTERIOR>
+__device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const float* __restrict__ xin, const UpfirdnParams& p,
+                                               const unsigned long long (&kx)[4], const unsigned long long (&ky)[4],
+                                               int ox0, int ix0, int oy0, int oy1, const float4& b4) {
+  const int64_t orow = (int64_t)p.out_w * p.minor;
+  const int64_t irow = (int64_t)p.in_w * p.minor;
+  bool colok[XT + 3];
+#pragma unroll
+  for (int i = 0; i < XT + 3; ++i) colok[i] = INTERIOR || ((ix0 + i) >= 0 && (ix0 + i) < p.in_w);
+  f2x2 w[4][XT];   // horizontal results of the last four input rows (slot = row & 3 after unrolling)
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int j = 0; j < XT; ++j) w[s][j] = f2x2{0ull, 0ull};
+  const int iy_begin = oy0 - p.pad_y0;
+  const int iy_end = oy1 - 1 - p.pad_y0 + 3;
+  const float* rp = xin + (int64_t)iy_begin * irow + (int64_t)ix0 * p.minor;
+  float* op = o + (int64_t)(oy0 - 3) * orow;   // output row completed by input row iy is iy + pad - 3
+  int oy = oy0 - 3;
+  for (int iy = iy_begin; iy <= iy_end; iy += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (iy + u <= iy_end) {
+        const bool rowok = INTERIOR || ((iy + u) >= 0 && (iy + u) < p.in_h);
+        f2x2 r[XT + 3];
+#pragma unroll
+        for (int i = 0; i < XT + 3; ++i)
+          r[i] = (rowok && colok[i]) ? ldg_f2x2(rp + (int64_t)i * p.minor) : f2x2{0ull, 0ull};
+#pragma unroll
+        for (int j = 0; j < XT; ++j) {
+          f2x2 a;
+          a.lo = fma2(r[j + 3].lo, kx[3], fma2(r[j + 2].lo, kx[2], fma2(r[j + 1].lo, kx[1], mul2(r[j].lo, kx[0]))));
+          a.hi = fma2(r[j + 3].hi, kx[3], fma2(r[j + 2].hi, kx[2], fma2(r[j + 1].hi, kx[1], mul2(r[j].hi, kx[0]))));
+          w[u][j] = a;   // slot u holds row iy+u; slots (u+1)&3, (u+2)&3, (u+3)&3 hold rows -3, -2, -1
+          if (oy >= oy0 && (INTERIOR || ox0 + j < p.out_w)) {
+            const f2x2& w0 = w[(u + 1) & 3][j];
+            const f2x2& w1 = w[(u + 2) & 3][j];
+            const f2x2& w2 = w[(u + 3) & 3][j];
+            const unsigned long long dl = fma2(a.lo, ky[3], fma2(w2.lo, ky[2], fma2(w1.lo, ky[1], mul2(w0.lo, ky[0]))));
+            const unsigned long long dh = fma2(a.hi, ky[3], fma2(w2.hi, ky[2], fma2(w1.hi, ky[1], mul2(w0.hi, ky[0]))));
+            float4 done;
+            unpack2(dl, done.x, done.y);
+            unpack2(dh, done.z, done.w);
+            if (EPI) {
+              done.x = lrelu(done.x + b4.x, p.alpha) * p.gain;
+              done.y = lrelu(done.y + b4.y, p.alpha) * p.gain;
+              done.z = lrelu(done.z + b4.z, p.alpha) * p.gain;
+              done.w = lrelu(done.w + b4.w, p.alpha) * p.gain;
+            }
+            st_stream4(op + (int64_t)j * p.minor, done);
+          }
+        }
+        rp += irow;
+        op += orow;
+        ++oy;
+      }
+    }
+  }
+}
+
+template <int ROWS, int XT, bool EPI>
+__global__ void __launch_bounds__(128) blur4_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                         const float* __restrict__ kernel,
+                                                         const float* __restrict__ bias, UpfirdnParams p) {
+  // taps: flipped (true convolution) and zero-extended to 4x4; 16 uniform loads per thread
+  Taps4 tp;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      tp.k[a][b] = (a < p.kh && b < p.kw) ? __ldg(kernel + (p.kh - 1 - a) * p.kw + (p.kw - 1 - b)) : 0.f;
+  // separable? (exact test: the binomial taps are small integers / 2^k, so rank 1 holds bit-exactly)
+  bool sep = tp.k[0][0] != 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) sep = sep && (tp.k[a][b] * tp.k[0][0] == tp.k[a][0] * tp.k[0][b]);
+  if (!sep) {
+    blur4_general<ROWS, XT, EPI>(out, x, bias, p, tp);
+    return;
+  }
+  unsigned long long kx[4], ky[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float cv = tp.k[i][0] / tp.k[0][0];
+    kx[i] = pack2(tp.k[0][i], tp.k[0][i]);
+    ky[i] = pack2(cv, cv);
+  }
+  const int c4n = p.minor >> 2;
+  const int groups = (p.out_w + XT - 1) / XT;
+  const int lin = blockIdx.x * blockDim.x + threadIdx.x;  // (column group, c4), c4 fastest
+  if (lin >= groups * c4n) return;
+  const int og = lin / c4n;
+  const int c = (lin - og * c4n) << 2;
+  const int ox0 = og * XT;
+  const int m = blockIdx.z;
+  const int oy0 = blockIdx.y * ROWS;
+  const int oy1 = min(oy0 + ROWS, p.out_h);
+  const int ix0 = ox0 - p.pad_x0;
+  const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
+  float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI) b4 = *reinterpret_cast<const float4*>(bias + c);
+  const bool interior = ix0 >= 0 && ix0 + XT + 3 <= p.in_w && ox0 + XT <= p.out_w && oy0 - p.pad_y0 >= 0 &&
+                        oy1 - 1 - p.pad_y0 + 3 < p.in_h;
+  if (interior) blur4sep_strip<XT, EPI, true>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4);
+  else blur4sep_strip<XT, EPI, false>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4);
+}
+
 }  // namespace ideas
 
 using namespace ideas;
@@ -204,9 +334,9 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
   if (fast) {
     const int c4n = minor / 4;
     constexpr int ROWS = 32, XT = 4;
-    dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 256), ceil_div(p.out_h, ROWS), major);
-    if (bias) blur4_nhwc_kernel<ROWS, XT, true><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
-    else blur4_nhwc_kernel<ROWS, XT, false><<<grid, 256, 0, st>>>(out, x, kernel, bias, p);
+    dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
+    if (bias) blur4_nhwc_kernel<ROWS, XT, true><<<grid, 128, 0, st>>>(out, x, kernel, bias, p);
+    else blur4_nhwc_kernel<ROWS, XT, false><<<grid, 128, 0, st>>>(out, x, kernel, bias, p);
     IDEAS_CHECK_LAUNCH("upfirdn2d(fast)");
     return IDEAS_OK;
   }

@@ -13,6 +13,8 @@ from ideas_b200._tensor import ptr, stream_ptr
 
 iters = int(os.environ.get("ITERS", "10"))
 dev = torch.device("cuda")
+if "IDEAS_HALO" in os.environ:
+    _lib.call("ideas_set_option", b"halo", int(os.environ["IDEAS_HALO"]))
 
 
 def timeit(fn, n=iters, warm=2):
@@ -57,6 +59,11 @@ conv_suite(32, 128, 128, 256, tag="_g256")
 conv_suite(32, 64, 128, 258, pad=0, tag="_d256")
 conv_suite(32, 128, 256, 129, stride=2, pad=0, tag="_down")
 conv_suite(32, 512, 512, 16, tag="_g16")
+conv_suite(32, 256, 256, 128, tag="_g128")
+conv_suite(32, 512, 512, 32, tag="_g32")
+conv_suite(32, 256, 512, 64, tag="_d64")
+if os.environ.get("CONV_ONLY"):
+    sys.exit(0)
 
 # blur (cfg 2)
 B, Cb, Hb = 32, 128, 256
@@ -72,6 +79,14 @@ y2 = torch.empty(B, Hb - 1, Hb - 1, Cb, device=dev)
 t = timeit(lambda: _lib.call("ideas_upfirdn2d", ptr(y2), ptr(xb), ptr(kk), B, Hb, Hb, Cb, 4, 4, 1, 1, 1, 1, 1, 1, 1, 1, ptr(None), 0.2, 1.0,
                              stream_ptr(xb)), n=20)
 print(json.dumps({"kernel": "blur_pad11", "ms": t * 1e3, "gbs": 4.0 * (xb.numel() + y2.numel()) / t / 1e9}))
+for (Bq, Cq, Hq, pd) in ((32, 64, 256, 1), (32, 256, 128, 2), (96, 512, 32, 2), (32, 32, 256, 2)):
+    xq = torch.randn(Bq, Hq, Hq, Cq, device=dev)
+    Ho = Hq + 2 * pd - 3
+    yq = torch.empty(Bq, Ho, Ho, Cq, device=dev)
+    t = timeit(lambda: _lib.call("ideas_upfirdn2d", ptr(yq), ptr(xq), ptr(kk), Bq, Hq, Hq, Cq, 4, 4, 1, 1, 1, 1, pd, pd, pd, pd, ptr(None),
+                                 0.2, 1.0, stream_ptr(xq)), n=20)
+    print(json.dumps({"kernel": f"blur_{Bq}x{Cq}x{Hq}_pad{pd}", "ms": t * 1e3, "gbs": 4.0 * (xq.numel() + yq.numel()) / t / 1e9}))
+    del xq, yq
 # bias + lrelu forward / backward (cfg 2 iii)
 bias = torch.randn(Cb, device=dev)
 out = torch.empty_like(xb)

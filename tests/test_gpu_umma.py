@@ -159,6 +159,81 @@ def test_umma_wgrad_matches_simt(case):
     assert rel(got, ref) <= 1e-3, rel(got, ref)
 
 
+# ---------------------------------------------------------------------------------------------
+# halo-reuse kernel (conv_umma_halo_kernel): forced on ("halo" = 2) for every eligible launch and
+# compared with the FFMA kernel; shapes cover ragged tiles in x and y, pad 0 / pad 1 tap sets, 2x2
+# filters, channel counts that leave the 128-row weight tile partly empty, and the stride-2 data
+# gradient whose four output phases use 1/2/2/4 taps with a strided destination.
+class _halo:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        _lib().call("ideas_set_option", b"halo", self.mode)
+
+    def __exit__(self, *a):
+        _lib().call("ideas_set_option", b"halo", 1)
+
+
+HALO_FWD_CASES = [
+    # N, C, K, H, W, k, pad
+    (2, 32, 128, 16, 16, 3, 1),
+    (2, 64, 128, 16, 16, 3, 1),
+    (3, 128, 256, 32, 32, 3, 1),
+    (1, 512, 512, 64, 64, 3, 1),
+    (2, 128, 128, 66, 66, 3, 0),
+    (2, 96, 64, 20, 12, 3, 1),           # K = 64: half of the weight tile is TMA zero fill
+    (1, 32, 64, 256, 256, 3, 1),
+    (2, 64, 384, 37, 29, 3, 1),          # ragged in both directions, K = 3 x 128
+    (1, 128, 128, 130, 258, 3, 0),       # wide rows
+    (2, 64, 160, 9, 50, 3, 1),           # K = 160: second k-tile has 32 live rows
+    (4, 384, 384, 14, 14, 3, 1),         # narrowest eligible rows (bwp = 16)
+    (4, 768, 384, 17, 17, 2, 0),         # 2x2 valid conv (Dco head shape, larger image)
+]
+
+
+@pytest.mark.parametrize("case", HALO_FWD_CASES)
+def test_halo_forward_matches_simt(case):
+    L = _lib()
+    N, C, K, H, W, k, pad = case
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g)
+    wp = torch.randn(k * k, K, C, device="cuda", generator=g) / (C * k * k) ** 0.5
+    d = torch.rand(N, K, device="cuda", generator=g) + 0.5
+    b = torch.randn(K, device="cuda", generator=g)
+    ref = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_SIMT, d, b, 1)
+    n0 = L.launch_count()
+    with _halo(2):
+        got = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA, d, b, 1)
+        plain = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA)
+    torch.cuda.synchronize()
+    assert L.launch_count() - n0 == 2
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+    assert rel(plain, conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_SIMT)) <= 1e-3
+    with _halo(0):
+        old = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA, d, b, 1)
+    # same tf32 products, different summation order only
+    assert rel(got, old) <= 2e-5, rel(got, old)
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES + [(2, 128, 128, 64, 64, 3, 1, 1), (1, 256, 128, 40, 24, 3, 1, 1)])
+def test_halo_dgrad_matches_simt(case):
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(6)
+    dy = torch.randn(N, OH, OW, K, device="cuda", generator=g)
+    wpt = torch.randn(k * k, C, K, device="cuda", generator=g) / (K * k * k) ** 0.5
+    s = torch.rand(N, C, device="cuda", generator=g) + 0.5
+    ref = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_SIMT, s)
+    with _halo(2):
+        got = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_AUTO, s)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+
+
 def test_tf32_error_level_vs_fp64():
     """The tensor path multiplies in TF32 (10-bit mantissa) and accumulates in fp32: report and bound
     its error against an fp64 convolution at the cfg-3 reduction length (K = 9 * 512)."""

@@ -290,29 +290,32 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
 
 // ==========================================================================================
 // Halo-reuse kernel (source stride 1, several taps): the implicit GEMM above fetches every shifted
-// 128-pixel patch again for each filter tap -- 9x the activation bytes of a 3x3 filter through L2,
-// and L2->SM bandwidth (~6300 B/clk chip-wide) is what bounds it.  Here the roles are swapped:
+// 128-pixel patch again for each filter tap -- 9x the activation bytes of a 3x3 filter through L2 --
+// and its prologue/epilogue are exposed once per CTA.  Here the roles are swapped,
 //   D[k, pixel] = sum_{tap, c} Wp[tap][k][c] * X[pixel + tap, c]        (M = 128 output channels,
 //                                                                        N = pixels of the tile)
-// and ONE halo'd activation slab per 32-channel step -- a TMA box of (bh*pb + halo_y) image rows x
+// and ONE halo'd activation slab per 32-channel step -- a TMA box of (bh + halo_y) image rows x
 // (bw + halo_x) columns, rows of 128 B in K-major SWIZZLE_128B -- serves every tap: the B descriptor
 // of tap (dy,dx) simply starts (dy*bwp + dx) rows further (tcgen05 computes the swizzle from the
 // address bits, so a start address that is not 1024-byte aligned is legal with base_offset 0;
 // scripts/probe_umma_offset.cu is the measurement).  The N extent therefore runs over the padded
-// row width bwp: the halo_x columns of every row produce outputs that are dropped, (bw/bwp of the
-// MMA work is useful), in exchange for ~9x fewer activation bytes.  Each CTA owns 128 output
-// channels x pb pixel blocks (pb*N <= 512 TMEM columns), so a 16 KB weight tile feeds pb MMAs.
-//   warp 0: weight-tile TMA producer (ring of kHaloWStages x 16 KB)
-//   warp 1: MMA issuer + TMEM owner
-//   warp 2 lane 0: activation-slab TMA producer (2 slots), then epilogue with warps 2..9
-//   epilogue: tcgen05.ld (lane = output channel, column = pixel) -> d[n,k] -> +bias -> lrelu*gain ->
-//             NHWC stores (a warp writes 32 consecutive channels of one pixel: 128 B)
+// row width bwp: the halo_x columns of every row produce outputs that are dropped (bw/bwp of the
+// MMA work is useful) in exchange for ~9x fewer activation bytes.
+// The kernel is persistent (one CTA per SM walks a static list of (k-tile, pixel-tile) items) with
+// two TMEM accumulator buffers, so the epilogue of item i overlaps the main loop of item i+1 and
+// the TMA producers run ahead across items:
+//   warp 0      weight-tile TMA producer (ring of up to kHaloMaxWStages x 16 KB)
+//   warp 1      activation-slab TMA producer (ring of 2-3 slabs)
+//   warp 2      MMA issuer + TMEM owner
+//   warps 3..10 epilogue: tcgen05.ld (lane = output channel, column = pixel) -> d[n,k] -> +bias ->
+//               lrelu*gain -> NHWC stores (a warp writes 32 consecutive channels of one pixel: 128 B)
 // ==========================================================================================
-constexpr int kHaloWStages = 4;
-constexpr int kHaloThreads = 320;            // warps 0/1 producers + MMA, warps 2..9 epilogue
+constexpr int kHaloMaxWStages = 12;         // weight ring: as deep as shared memory allows (TMA latency >> one tap)
+constexpr int kHaloThreads = 352;
+constexpr int kHaloEpiWarps = 8;
 constexpr uint32_t kHaloWBytes = 128 * 128;   // 128 output channels x 32 fp32 input channels
 constexpr int kHaloSlack = 24;                // rows past the box that rounding N up to 16 may touch
-constexpr uint32_t kHaloMaxSlot = 80 * 1024;
+constexpr uint32_t kHaloSmemBudget = 224 * 1024;
 
 std::atomic<int> g_halo_mode{1};              // 0 = never, 1 = heuristic, 2 = whenever eligible
 
@@ -330,53 +333,67 @@ struct alignas(64) HaloParams {
   int N, QH, QW;
   int OH, OW, OC;
   int o_s, o_py, o_px;
-  int bw, bwp, bh, pb;
+  int bw, bwp, bh;
   int nmma, box_rows;
   int x_org, y_org;
-  int tiles_x, tiles_y;
+  int tiles_x, tiles_y, ktiles, items;
   int ntaps, csteps;
-  uint32_t x_slot_bytes, x_tx_bytes, tmem_cols;
+  int x_stages, w_stages;
+  uint32_t x_slot_bytes, x_tx_bytes;
   int act;
   float alpha, gain;
   TapH taps[kMaxTaps];
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t wfull[kHaloWStages];
-  __shared__ __align__(8) uint64_t wempty[kHaloWStages];
-  __shared__ __align__(8) uint64_t xfull[2];
-  __shared__ __align__(8) uint64_t xempty[2];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t wfull[kHaloMaxWStages];
+  __shared__ __align__(8) uint64_t wempty[kHaloMaxWStages];
+  __shared__ __align__(8) uint64_t xfull[3];
+  __shared__ __align__(8) uint64_t xempty[3];
+  __shared__ __align__(8) uint64_t tfull[2];
+  __shared__ __align__(8) uint64_t tempty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t wring = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t xring = wring + kHaloWStages * kHaloWBytes;
-  const int k0 = blockIdx.x * 128;
-  const int bx = blockIdx.y % p.tiles_x;
-  const int tt = blockIdx.y / p.tiles_x;
-  const int qx0 = bx * p.bw;
-  const int qy0 = (tt % p.tiles_y) * (p.pb * p.bh);
-  const int n = tt / p.tiles_y;
+  const uint32_t xring = wring + p.w_stages * kHaloWBytes;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kHaloWStages; ++s) {
+    for (int s = 0; s < kHaloMaxWStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&wfull[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&wempty[s]), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       ptx::mbar_init(ptx::smem_u32(&xfull[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&xempty[s]), 1);
     }
-    ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty[s]), kHaloEpiWarps);
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), p.tmem_cols);
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+
+  // item -> (k-tile, pixel tile); the k-tile runs fastest so that concurrently running CTAs share activations
+#define IDEAS_HALO_DECODE(item)                         \
+  const int kt = (item) % p.ktiles;                     \
+  const int pt = (item) / p.ktiles;                     \
+  const int bx = pt % p.tiles_x;                        \
+  const int tt = pt / p.tiles_x;                        \
+  const int qx0 = bx * p.bw;                            \
+  const int qy0 = (tt % p.tiles_y) * p.bh;              \
+  const int n = tt / p.tiles_y;                         \
+  const int k0 = kt * 128;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -384,115 +401,138 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
       ptx::tma_prefetch_desc(&p.w);
       int stage = 0;
       uint32_t phase = 0;
-      for (int cs = 0; cs < p.csteps; ++cs)
-        for (int t = 0; t < p.ntaps; ++t) {
-          ptx::mbar_wait(ptx::smem_u32(&wempty[stage]), phase ^ 1u);
-          const uint32_t fb = ptx::smem_u32(&wfull[stage]);
-          ptx::mbar_arrive_expect_tx(fb, kHaloWBytes);
-          ptx::tma_load_3d(wring + stage * kHaloWBytes, &p.w, fb, cs * kBlockK, k0, p.taps[t].widx);
-          if (++stage == kHaloWStages) { stage = 0; phase ^= 1u; }
-        }
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int k0 = (item % p.ktiles) * 128;
+        for (int cs = 0; cs < p.csteps; ++cs)
+          for (int t = 0; t < p.ntaps; ++t) {
+            ptx::mbar_wait(ptx::smem_u32(&wempty[stage]), phase ^ 1u);
+            const uint32_t fb = ptx::smem_u32(&wfull[stage]);
+            ptx::mbar_arrive_expect_tx(fb, kHaloWBytes);
+            ptx::tma_load_3d(wring + stage * kHaloWBytes, &p.w, fb, cs * kBlockK, k0, p.taps[t].widx);
+            if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
+          }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = ptx::idesc_tf32(128, p.nmma, 0, 0);
+      // ===== activation slabs: one halo'd box per 32-channel step =====
+      ptx::tma_prefetch_desc(&p.src);
       int stage = 0;
       uint32_t phase = 0;
-      for (int cs = 0; cs < p.csteps; ++cs) {
-        const int xs = cs & 1;
-        ptx::mbar_wait(ptx::smem_u32(&xfull[xs]), (uint32_t)(cs >> 1) & 1u);
-        const uint32_t xa = xring + xs * p.x_slot_bytes;
-        for (int t = 0; t < p.ntaps; ++t) {
-          ptx::mbar_wait(ptx::smem_u32(&wfull[stage]), phase);
-          ptx::tc_fence_after();
-          const uint64_t adesc = ptx::smem_desc_sw128(wring + stage * kHaloWBytes, 16, 1024);
-          for (int j = 0; j < p.pb; ++j) {
-            const uint64_t bdesc = ptx::smem_desc_sw128(xa + (uint32_t)(j * p.bh * p.bwp + p.taps[t].rowoff) * 128u, 16, 1024);
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        IDEAS_HALO_DECODE(item)
+        (void)k0;
+        for (int cs = 0; cs < p.csteps; ++cs) {
+          ptx::mbar_wait(ptx::smem_u32(&xempty[stage]), phase ^ 1u);
+          const uint32_t fb = ptx::smem_u32(&xfull[stage]);
+          ptx::mbar_arrive_expect_tx(fb, p.x_tx_bytes);
+          ptx::tma_load_4d(xring + stage * p.x_slot_bytes, &p.src, fb, cs * kBlockK, qx0 + p.x_org, qy0 + p.y_org, n);
+          if (++stage == p.x_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ptx::idesc_tf32(128, p.nmma, 0, 0);
+      int ws = 0, xs = 0;
+      uint32_t wphase = 0, xphase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty[buf]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * 256;
+        for (int cs = 0; cs < p.csteps; ++cs) {
+          ptx::mbar_wait(ptx::smem_u32(&xfull[xs]), xphase);
+          const uint32_t xa = xring + xs * p.x_slot_bytes;
+          for (int t = 0; t < p.ntaps; ++t) {
+            ptx::mbar_wait(ptx::smem_u32(&wfull[ws]), wphase);
+            ptx::tc_fence_after();
+            const uint64_t adesc = ptx::smem_desc_sw128(wring + ws * kHaloWBytes, 16, 1024);
+            const uint64_t bdesc = ptx::smem_desc_sw128(xa + (uint32_t)p.taps[t].rowoff * 128u, 16, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              ptx::mma_tf32(tmem_base + j * p.nmma, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cs | t | k) != 0));
+              ptx::mma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cs | t | k) != 0));
+            ptx::mma_commit(ptx::smem_u32(&wempty[ws]));
+            if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
           }
-          ptx::mma_commit(ptx::smem_u32(&wempty[stage]));
-          if (++stage == kHaloWStages) { stage = 0; phase ^= 1u; }
+          ptx::mma_commit(ptx::smem_u32(&xempty[xs]));   // the slab is free once every tap has consumed it
+          if (++xs == p.x_stages) { xs = 0; xphase ^= 1u; }
         }
-        ptx::mma_commit(ptx::smem_u32(&xempty[xs]));   // the slab is free once every tap has consumed it
+        ptx::mma_commit(ptx::smem_u32(&tfull[buf]));
       }
-      ptx::mma_commit(ptx::smem_u32(&accum_bar));
     }
   } else {
-    if (warp == 2 && lane == 0) {
-      // ===== activation slabs: one halo'd box per 32-channel step, double buffered =====
-      ptx::tma_prefetch_desc(&p.src);
-      for (int cs = 0; cs < p.csteps; ++cs) {
-        const int xs = cs & 1;
-        ptx::mbar_wait(ptx::smem_u32(&xempty[xs]), ((uint32_t)(cs >> 1) & 1u) ^ 1u);
-        const uint32_t fb = ptx::smem_u32(&xfull[xs]);
-        ptx::mbar_arrive_expect_tx(fb, p.x_tx_bytes);
-        ptx::tma_load_4d(xring + xs * p.x_slot_bytes, &p.src, fb, cs * kBlockK, qx0 + p.x_org, qy0 + p.y_org, n);
-      }
-    }
-    __syncwarp();
-    // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4 (lane = output channel); the two warps of a
+    // ===== epilogue: warps 3..10; TMEM lane quarter = warp % 4 (lane = output channel); the two warps of a
     // quarter take alternate 16-column chunks.  Within a chunk the 16 pixels span at most two tile rows
     // (bwp >= 16), so every address is an independent function of the chunk origin: no serial chain. =====
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int k = k0 + quarter * 32 + lane;
-    const bool kok = k < p.OC;
-    float os = 1.f, bs = 0.f;
-    if (kok) {
-      if (p.out_scale) os = __ldg(p.out_scale + (int64_t)n * p.OC + k);
-      if (p.bias) bs = __ldg(p.bias + k);
-    }
+    const int half = (warp - 3) >> 2;
     const int npix = p.bh * p.bwp;
-    const int chunks_per_blk = (npix + 15) >> 4;
-    const int total_chunks = p.pb * chunks_per_blk;
-    const int xlim = min(p.bw, p.QW - qx0);
+    const int chunks = (npix + 15) >> 4;
     const int pix_step = p.o_s * p.OC;
     const int row_step = p.o_s * p.OW * p.OC;
     const bool lrelu_on = p.act == IDEAS_ACT_LRELU;
     const float alpha = p.alpha, gain = lrelu_on ? p.gain : 1.f;
-    float* base = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + k;
-    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
-    ptx::tc_fence_after();
-    for (int c = half; c < total_chunks; c += 2) {
-      const int j = c / chunks_per_blk;
-      const int m0 = (c - j * chunks_per_blk) << 4;
-      const int y0 = m0 / p.bwp;
-      const int x0 = m0 - y0 * p.bwp;
-      const int ylim = min(p.bh, p.QH - qy0 - j * p.bh);   // rows of this pixel block inside the image
-      float v[16];
-      ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * p.nmma + m0), v);
-      float* r0 = base + (int64_t)(j * p.bh + y0) * row_step;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        int xi = x0 + i;
-        const int wrap = xi >= p.bwp ? 1 : 0;
-        xi -= wrap ? p.bwp : 0;
-        const bool ok = kok && xi < xlim && (y0 + wrap) < ylim;
-        float r = fmaf(v[i], os, bs);
-        r = (lrelu_on && r < 0.f) ? r * alpha : r;
-        r *= gain;
-        if (ok) r0[wrap * row_step + xi * pix_step] = r;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      IDEAS_HALO_DECODE(item)
+      const int buf = it & 1;
+      const int k = k0 + quarter * 32 + lane;
+      const bool kok = k < p.OC;
+      float os = 1.f, bs = 0.f;
+      if (kok) {
+        if (p.out_scale) os = __ldg(p.out_scale + (int64_t)n * p.OC + k);
+        if (p.bias) bs = __ldg(p.bias + k);
       }
+      const int xlim = min(p.bw, p.QW - qx0);
+      const int ylim = min(p.bh, p.QH - qy0);
+      float* base = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + k;
+      ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      for (int c = half; c < chunks; c += 2) {
+        const int m0 = c << 4;
+        const int y0 = m0 / p.bwp;
+        const int x0 = m0 - y0 * p.bwp;
+        float v[16];
+        ptx::tmem_ld_32x16(acc + (uint32_t)m0, v);
+        float* r0 = base + (int64_t)y0 * row_step;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int xi = x0 + i;
+          const int wrap = xi >= p.bwp ? 1 : 0;
+          xi -= wrap ? p.bwp : 0;
+          const bool ok = kok && xi < xlim && (y0 + wrap) < ylim;
+          float r = fmaf(v[i], os, bs);
+          r = (lrelu_on && r < 0.f) ? r * alpha : r;
+          r *= gain;
+          if (ok) r0[wrap * row_step + xi * pix_step] = r;
+        }
+      }
+      // every tcgen05.ld of this warp has completed (wait::ld): hand the accumulator back
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ptx::smem_u32(&tempty[buf]));
     }
   }
+#undef IDEAS_HALO_DECODE
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
 struct HaloTile {
-  int bw, bwp, bh, pb, nmma, tiles_x, tiles_y;
+  int bw, bwp, bh, nmma, tiles_x, tiles_y, x_stages, w_stages;
   uint32_t slot_bytes;
-  double cycles;   // modelled cycles per 32-channel step over the whole q grid (one image)
+  double cycles;   // modelled cycles per 32-channel step over the q grid of one image
 };
 
-// Pick (bw, bh, pb) minimising modelled time = tiles * max(MMA cycles, L2-feed cycles) per channel step.
+// Pick (bw, bh) minimising modelled time = tiles * max(MMA cycles, L2-feed cycles) per channel step.
 bool choose_halo_tile(int QW, int QH, int hx, int hy, int ntaps, HaloTile* out) {
   struct Key { int a, b, c, d, e; bool operator<(const Key& o) const { return memcmp(this, &o, sizeof(Key)) < 0; } };
   static std::mutex mu;
@@ -505,26 +545,26 @@ bool choose_halo_tile(int QW, int QH, int hx, int hy, int ntaps, HaloTile* out) 
   }
   HaloTile best{};
   best.bw = 0; best.cycles = 1e300;
-  for (int pb = 1; pb <= 2; ++pb)
-    for (int bw = 4; bw <= QW && bw + hx <= 256; ++bw) {
-      const int bwp = bw + hx;
-      if (bwp < 16) continue;   // the epilogue assumes a 16-pixel chunk spans at most two rows
-      for (int bh = 1; bh * bwp <= 256 && (bh - 1) * pb < QH; ++bh) {
-        const int nmma = ((bh * bwp + 15) / 16) * 16;
-        const int rows = pb * bh + hy;
-        if (rows > 256) break;
-        const uint32_t slot = (uint32_t)((rows * bwp + hx + kHaloSlack) * 128 + 1023) & ~1023u;
-        if (slot > kHaloMaxSlot) break;
-        const int tx = ceil_div(QW, bw), ty = ceil_div(QH, pb * bh);
-        const double mma = (double)ntaps * pb * 4 * (nmma / 2.0);
-        const double l2 = ((double)ntaps * kHaloWBytes + (double)rows * bwp * 128) / 42.0;
-        const double cyc = (double)tx * ty * (mma > l2 ? mma : l2) + (double)tx * ty * 40.0;   // + fixed cost per CTA
-        if (cyc < best.cycles) {
-          best.bw = bw; best.bwp = bwp; best.bh = bh; best.pb = pb; best.nmma = nmma; best.tiles_x = tx; best.tiles_y = ty;
-          best.slot_bytes = slot; best.cycles = cyc;
-        }
+  for (int bw = 4; bw <= QW && bw + hx <= 256; ++bw) {
+    const int bwp = bw + hx;
+    if (bwp < 16) continue;   // the epilogue assumes a 16-pixel chunk spans at most two rows
+    for (int bh = 1; bh * bwp <= 256 && bh - 1 < QH; ++bh) {
+      const int nmma = ((bh * bwp + 15) / 16) * 16;
+      const int rows = bh + hy;
+      const uint32_t slot = (uint32_t)((rows * bwp + hx + kHaloSlack) * 128 + 1023) & ~1023u;
+      if (2 * slot + 4 * kHaloWBytes > kHaloSmemBudget) break;
+      const int tx = ceil_div(QW, bw), ty = ceil_div(QH, bh);
+      const double mma = (double)ntaps * 4 * (nmma / 2.0);
+      const double l2 = ((double)ntaps * kHaloWBytes + (double)rows * bwp * 128) / 48.0;
+      const double cyc = (double)tx * ty * ((mma > l2 ? mma : l2) + 24.0);
+      if (cyc < best.cycles) {
+        best.bw = bw; best.bwp = bwp; best.bh = bh; best.nmma = nmma; best.tiles_x = tx; best.tiles_y = ty;
+        best.slot_bytes = slot; best.cycles = cyc; best.x_stages = 2;
+        const int ws = (int)((kHaloSmemBudget - 2 * slot) / kHaloWBytes);
+        best.w_stages = ws > kHaloMaxWStages ? kHaloMaxWStages : ws;
       }
     }
+  }
   {
     std::lock_guard<std::mutex> lk(mu);
     cache[key] = best;
@@ -549,25 +589,31 @@ int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
   HaloTile tile;
   if (!choose_halo_tile(g.QW, g.QH, hx, hy, g.ntaps, &tile)) return IDEAS_ERR_UNSUPPORTED;
   if (mode == 1) {
-    // heuristic (scripts/kernels_microbench.py, IDEAS_HALO=0 vs 2): without an overlapped epilogue the halo
-    // kernel only wins where the pixel-major kernel's 128-pixel boxes straddle images (<= 16x16 maps)
-    if (g.OC < 128 || (g.OC % 128 != 0 && g.OC < 384) || g.QW > 16) return IDEAS_ERR_UNSUPPORTED;
+    // heuristic from scripts/kernels_microbench.py (IDEAS_HALO=0 vs 2): with <= 128 input channels the
+    // pixel-major kernel is bound by activation re-reads and by its exposed epilogue (halo kernel 1.2-1.7x);
+    // from 256 input channels on, weight tiles dominate the L2 traffic of both kernels and the halo columns
+    // only cost tensor work (0.8-0.95x).  Strided destinations (data gradients of stride-2 convs, 1-4 taps
+    // per phase) have short reductions, where the overlapped epilogue wins (1.25x).
+    if (g.OC < 64 || !(g.IC <= 128 || g.o_s == 2)) return IDEAS_ERR_UNSUPPORTED;
   }
 
   HaloParams p;
   p.dst = dst; p.out_scale = out_scale; p.bias = bias;
   p.N = g.N; p.QH = g.QH; p.QW = g.QW; p.OH = g.OH; p.OW = g.OW; p.OC = g.OC;
   p.o_s = g.o_s; p.o_py = g.o_py; p.o_px = g.o_px;
-  p.bw = tile.bw; p.bwp = tile.bwp; p.bh = tile.bh; p.pb = tile.pb; p.nmma = tile.nmma;
-  p.box_rows = tile.pb * tile.bh + hy;
+  p.bw = tile.bw; p.bwp = tile.bwp; p.bh = tile.bh; p.nmma = tile.nmma;
+  p.box_rows = tile.bh + hy;
   p.x_org = min_dx; p.y_org = min_dy;
   p.tiles_x = tile.tiles_x; p.tiles_y = tile.tiles_y;
+  p.ktiles = ceil_div(g.OC, 128);
+  const int64_t items = (int64_t)g.N * p.tiles_y * p.tiles_x * p.ktiles;
+  if (items > (1ll << 30)) return IDEAS_ERR_UNSUPPORTED;
+  p.items = (int)items;
   p.ntaps = g.ntaps; p.csteps = g.IC / kBlockK;
+  p.x_stages = tile.x_stages;
+  p.w_stages = tile.w_stages;
   p.x_slot_bytes = tile.slot_bytes;
   p.x_tx_bytes = (uint32_t)(p.box_rows * p.bwp * 128);
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(p.pb * p.nmma)) cols <<= 1;
-  p.tmem_cols = cols;
   p.act = act; p.alpha = alpha; p.gain = gain;
   for (int t = 0; t < g.ntaps; ++t) {
     p.taps[t].rowoff = (g.taps[t].dy - min_dy) * p.bwp + (g.taps[t].dx - min_dx);
@@ -587,17 +633,15 @@ int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
     int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
     if (rc) return rc;
   }
-  const uint32_t smem = kHaloWStages * kHaloWBytes + 2 * p.x_slot_bytes + 1024;
+  const uint32_t smem = p.w_stages * kHaloWBytes + p.x_stages * p.x_slot_bytes + 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kHaloWStages * kHaloWBytes + 2 * kHaloMaxSlot + 1024);
+                                    kHaloSmemBudget + 1024);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_halo: cudaFuncSetAttribute");
-  const int64_t ytiles = (int64_t)g.N * p.tiles_y * p.tiles_x;
-  if (ytiles > 65535) return IDEAS_ERR_UNSUPPORTED;
-  dim3 grid(ceil_div(g.OC, 128), (unsigned)ytiles);
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
   conv_umma_halo_kernel<<<grid, kHaloThreads, smem, st>>>(p);
   IDEAS_CHECK_LAUNCH("conv_umma_halo");
   return IDEAS_OK;

@@ -724,71 +724,84 @@ int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
 // weight gradient:  dWp[tap][k][c] += sum_pixels dY[pixel, k] * X[pixel*stride + tap, c]
 //   GEMM per tap with M = 128 output channels, N = BNC input channels, reduction over pixels.
 //   Both operands are "MN-major": the reduction index (pixel) is the row of the NHWC tensors and the
-//   GEMM M/N index (channel) is contiguous.  One 5-D TMA box (32 ch x bw x bh x bn pixels x channel
-//   groups) per operand lands [channel group][32 pixels][32 ch] in shared memory, which is the
-//   MN-major canonical layout.  For 32-bit MN-major operands tcgen05 accepts only the "128 B swizzle
-//   with 32 B atom" pattern (descriptor layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
-//   LBO = stride between 32-channel groups (4 KB), SBO = stride between 4-pixel groups (512 B); each
-//   tcgen05.mma consumes 8 pixels (K = 8 for tf32).
-//   grid = (k-tiles * c-tiles, taps, pixel splits); partial sums are merged with vector red.add.
+//   GEMM M/N index (channel) is contiguous.  One 5-D TMA box (32 ch x pixels x channel groups) per
+//   operand lands [channel group][pixel][32 ch] in shared memory, which is the MN-major canonical
+//   layout.  For 32-bit MN-major operands tcgen05 accepts only the "128 B swizzle with 32 B atom"
+//   pattern (descriptor layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): LBO = stride between
+//   32-channel groups, SBO = stride between 4-pixel groups (512 B); each tcgen05.mma consumes 8
+//   pixels (K = 8 for tf32).
+//   Tap reuse (stride-1 convs): a CTA owns a GROUP of taps -- all of them when ntaps*BNC <= 512 TMEM
+//   columns, else one filter row -- with one accumulator per tap.  The dY tile of a 32-pixel box is
+//   loaded once per group, and ONE halo'd X box (bw+halo_x columns, bh+halo_y rows) serves every
+//   tap of the group: tap (dy,dx) starts its B descriptor (dy*xbw + dx) rows further (address-based
+//   swizzle: scripts/probe_umma_mn_offset.cu).  The 8 pixels of one MMA are 8 consecutive box
+//   columns (bw is a multiple of 8), so no reduction index is wasted.  Without it every tap re-read
+//   both operands through L2 (9x for a 3x3 filter), which bounded the kernel at 20-40 % of the tensor peak
+//   for <= 128 channels.  Stride-2 convs keep one tap per group (per-parity tensor maps).
+//   grid = (k-tiles * c-tiles, tap groups, pixel splits); partial sums are merged with vector red.add.
 // ==========================================================================================
 namespace {
 
 constexpr int kWgPix = 32;                       // pixels per k-block
 constexpr uint32_t kWgABytes = 4 * kWgPix * 128; // 128 output channels
+constexpr int kWgMaxStages = 8;
+constexpr int kWgMaxGroupTaps = 9;
+
+struct TapGroup {
+  int16_t oy, ox;        // box origin offset in the addressed x map
+  int16_t map;           // which x tensor map (parity)
+  int16_t ntaps;
+  int16_t drow[kWgMaxGroupTaps];   // row offset of the tap inside the x box
+  int16_t widx[kWgMaxGroupTaps];
+};
 
 struct alignas(64) WgradParams {
   CUtensorMap dy;        // (32, OW, OH, N, OC/32)
   CUtensorMap x[4];      // (32, Wd, Hd, N, IC/32) per parity
   float* dwp;
-  int OC, IC;
-  int bw, bh, bn;        // pixel box, bw*bh*bn == 32
+  int OC, IC, bnc;
+  int bw, bh, bn;        // pixel box of dY, bw*bh*bn == 32
   int tiles_x, tiles_y, nboxes;
   int boxes_per_split;
   int ctiles;
-  TapU taps[kMaxTaps];
-};
-
-template <int BNC> struct WgCfg {
-  static constexpr uint32_t kBBytes = (BNC / 32) * kWgPix * 128;
-  static constexpr uint32_t kStageBytes = kWgABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
-  static constexpr uint32_t kTmemCols = BNC < 32 ? 32 : BNC;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+  int stages;
+  uint32_t x_group_bytes;   // bytes of one 32-channel group of the x box
+  uint32_t stage_bytes, tmem_cols;
+  int rowbase[kWgPix / 8];  // x-box row of the first pixel of each 8-pixel MMA step
+  TapGroup groups[kMaxTaps];
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BNC>
+template <int T>   // taps per group (upper bound; groups may hold fewer)
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using Cfg = WgCfg<BNC>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
-  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t full_bar[kWgMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int ktile = blockIdx.x / p.ctiles, ctile = blockIdx.x - ktile * p.ctiles;
-  const int k0 = ktile * 128, c0 = ctile * BNC;
-  const TapU tp = p.taps[blockIdx.y];
+  const int k0 = ktile * 128, c0 = ctile * p.bnc;
+  const TapGroup& tg = p.groups[blockIdx.y];
   const int b_begin = blockIdx.z * p.boxes_per_split;
   const int b_end = min(b_begin + p.boxes_per_split, p.nboxes);
   const int nkb = b_end - b_begin;
   if (nkb <= 0) return;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < kWgMaxStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
     }
     ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), Cfg::kTmemCols);
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), p.tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -796,6 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_wgrad_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
+      const uint32_t tx_bytes = kWgABytes + (uint32_t)(p.bnc / 32) * p.x_group_bytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
@@ -805,30 +819,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_wgrad_kernel(const __gr
         const int qx0 = bx * p.bw, qy0 = (t % p.tiles_y) * p.bh, n0 = (t / p.tiles_y) * p.bn;
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
         const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-        ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
-        const uint32_t sa = tiles + stage * Cfg::kStageBytes;
+        ptx::mbar_arrive_expect_tx(fb, tx_bytes);
+        const uint32_t sa = tiles + stage * p.stage_bytes;
         ptx::tma_load_5d(sa, &p.dy, fb, 0, qx0, qy0, n0, k0 / 32);
-        ptx::tma_load_5d(sa + kWgABytes, &p.x[tp.map], fb, 0, qx0 + tp.ox, qy0 + tp.oy, n0, c0 / 32);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        ptx::tma_load_5d(sa + kWgABytes, &p.x[tg.map], fb, 0, qx0 + tg.ox, qy0 + tg.oy, n0, c0 / 32);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_tf32(128, BNC, 1, 1);
+      // The issuing thread is the critical path (an N = 64 MMA retires in ~32 clk): every descriptor is
+      // base + a precomputed 32-bit offset held in registers, the tap loop is unrolled at compile time.
+      const uint32_t idesc = ptx::idesc_tf32(128, p.bnc, 1, 1);
+      uint32_t boff[T][kWgPix / kUmmaK];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int k = 0; k < kWgPix / kUmmaK; ++k)
+          boff[t][k] = (uint32_t)((p.rowbase[k] + (t < tg.ntaps ? tg.drow[t] : 0)) * 128) >> 4;
+      const int ntaps = tg.ntaps;
+      const uint32_t bnc = p.bnc;
+      const uint64_t adesc0 = ptx::smem_desc_sw128_base32(tiles, kWgPix * 128, 512);
+      const uint64_t bdesc0 = ptx::smem_desc_sw128_base32(tiles + kWgABytes, p.x_group_bytes, 512);
+      const uint32_t stage_enc = p.stage_bytes >> 4;
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t senc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
         ptx::tc_fence_after();
-        const uint32_t sa = tiles + stage * Cfg::kStageBytes;
+        const uint64_t ad = adesc0 + senc, bd = bdesc0 + senc;
+        const uint32_t acc_flag = kb != 0;
 #pragma unroll
-        for (int k = 0; k < kWgPix / kUmmaK; ++k) {
-          const uint64_t adesc = ptx::smem_desc_sw128_base32(sa + k * 1024, kWgPix * 128, 512);
-          const uint64_t bdesc = ptx::smem_desc_sw128_base32(sa + kWgABytes + k * 1024, kWgPix * 128, 512);
-          ptx::mma_tf32(tmem_base, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+        for (int t = 0; t < T; ++t) {
+          if (t < ntaps) {
+#pragma unroll
+            for (int k = 0; k < kWgPix / kUmmaK; ++k)
+              ptx::mma_tf32(tmem_base + t * bnc, ad + (uint32_t)(k * 64), bd + boff[t][k], idesc, k ? 1u : acc_flag);
+          }
         }
         ptx::mma_commit(ptx::smem_u32(&empty_bar[stage]));
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        senc += stage_enc;
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; senc = 0; }
       }
       ptx::mma_commit(ptx::smem_u32(&accum_bar));
     }
@@ -837,13 +869,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_wgrad_kernel(const __gr
     const int k = k0 + quarter * 32 + lane;
     ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
     ptx::tc_fence_after();
-    float* dp = p.dwp + ((int64_t)tp.widx * p.OC + k) * p.IC + c0;
-    for (int ch = 0; ch < BNC / 32; ++ch) {
-      float v[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), v);
-      if (k < p.OC && c0 + ch * 32 < p.IC) {
+    for (int t = 0; t < tg.ntaps; ++t) {
+      float* dp = p.dwp + ((int64_t)tg.widx[t] * p.OC + k) * p.IC + c0;
+      for (int ch = 0; ch < p.bnc / 32; ++ch) {
+        float v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * p.bnc + ch * 32), v);
+        if (k < p.OC && c0 + ch * 32 < p.IC) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) red_add_v4(dp + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; i += 4) red_add_v4(dp + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
       }
     }
   }
@@ -851,36 +885,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_wgrad_kernel(const __gr
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
-void choose_box32(int N, int QH, int QW, int* bw, int* bh, int* bn, int* tx, int* ty, int* nboxes) {
-  long best = -1;
-  for (int w = 32; w >= 1; w >>= 1) {
-    if (w > pow2_ceil(QW) && w > 1) continue;
+// 32-pixel box (bw x bh x bn) covering the q grid with the fewest boxes weighted by the x halo overhead;
+// with tap reuse bw must be a multiple of 8 (one MMA = 8 consecutive box columns).
+void choose_box32(int N, int QH, int QW, int hx, int hy, bool reuse, int* bw, int* bh, int* bn, int* tx, int* ty, int* nboxes) {
+  double best = -1;
+  for (int w = 32; w >= (reuse ? 8 : 1); w >>= 1) {
+    if (w > pow2_ceil(QW) && w > (reuse ? 8 : 1)) continue;
     for (int h = 32 / w; h >= 1; h >>= 1) {
       if (h > pow2_ceil(QH) && h > 1) continue;
       const int n = 32 / (w * h);
       const long cnt = (long)ceil_div(QW, w) * ceil_div(QH, h) * ceil_div(N, n);
-      if (best < 0 || cnt < best) {
-        best = cnt; *bw = w; *bh = h; *bn = n; *tx = ceil_div(QW, w); *ty = ceil_div(QH, h);
+      // cost per box: the dY tile (128 channels x 32 pixels) plus the halo'd x tile
+      const double cost = (double)cnt * (32.0 + (double)(w + hx) * (h + hy) * n);
+      if (best < 0 || cost < best) {
+        best = cost; *bw = w; *bh = h; *bn = n; *tx = ceil_div(QW, w); *ty = ceil_div(QH, h);
+        *nboxes = (int)cnt;
       }
     }
   }
-  *nboxes = (int)best;
 }
 
-template <int BNC>
-int launch_wgrad(const WgradParams& p, dim3 grid, cudaStream_t st) {
-  using Cfg = WgCfg<BNC>;
+std::atomic<int> g_wgrad_reuse{1};
+
+template <int T>
+int launch_wgrad(const WgradParams& p, dim3 grid, uint32_t smem, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_umma_wgrad_kernel<BNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr_err = cudaFuncSetAttribute(conv_umma_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_wgrad: cudaFuncSetAttribute");
-  conv_umma_wgrad_kernel<BNC><<<grid, kThreads, Cfg::kSmemBytes, st>>>(p);
+  conv_umma_wgrad_kernel<T><<<grid, kThreads, smem, st>>>(p);
   IDEAS_CHECK_LAUNCH("conv_umma_wgrad");
   return IDEAS_OK;
 }
@@ -898,23 +937,92 @@ int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float
 
   WgradParams p;
   p.dwp = dwp; p.OC = g.OC; p.IC = g.IC;
-  choose_box32(g.N, g.QH, g.QW, &p.bw, &p.bh, &p.bn, &p.tiles_x, &p.tiles_y, &p.nboxes);
-  const int BNC = g.IC >= 256 && g.IC % 256 == 0 ? 256 : (g.IC > 64 ? 128 : (g.IC > 32 ? 64 : 32));
+  // ---- tap groups
+  int min_dx = 1 << 30, max_dx = -(1 << 30), min_dy = 1 << 30, max_dy = -(1 << 30);
+  for (int t = 0; t < g.ntaps; ++t) {
+    min_dx = g.taps[t].dx < min_dx ? g.taps[t].dx : min_dx; max_dx = g.taps[t].dx > max_dx ? g.taps[t].dx : max_dx;
+    min_dy = g.taps[t].dy < min_dy ? g.taps[t].dy : min_dy; max_dy = g.taps[t].dy > max_dy ? g.taps[t].dy : max_dy;
+  }
+  // tap reuse pays where activation/gradient re-reads bound the kernel (<= 128 input channels); wider layers
+  // keep one tap per CTA with a 256-channel N tile (measured: scripts/kernels_microbench.py)
+  const int reuse_mode = g_wgrad_reuse.load();
+  const bool reuse = reuse_mode && g.i_s == 1 && g.ntaps > 1 && g.QW >= 8 && (max_dx - min_dx) <= 4 &&
+                     (max_dy - min_dy) <= 4 && (g.IC <= 128 || reuse_mode == 2);
+  int BNC;
+  if (reuse) BNC = g.IC >= 128 && g.IC % 128 == 0 ? 128 : (g.IC % 64 == 0 ? 64 : 32);
+  else BNC = g.IC >= 256 && g.IC % 256 == 0 ? 256 : (g.IC > 64 ? 128 : (g.IC > 32 ? 64 : 32));
+  p.bnc = BNC;
   p.ctiles = ceil_div(g.IC, BNC);
   const int ktiles = ceil_div(g.OC, 128);
-
+  int ngroups = 0, hx = 0, hy = 0;
   bool need[4] = {false, false, false, false};
-  for (int t = 0; t < g.ntaps; ++t) {
-    const ConvTap& tp = g.taps[t];
-    int py = 0, px = 0, oy = tp.dy, ox = tp.dx;
-    if (g.i_s == 2) {
-      py = ((tp.dy % 2) + 2) % 2; px = ((tp.dx % 2) + 2) % 2;
-      oy = (tp.dy - py) / 2; ox = (tp.dx - px) / 2;
+  if (reuse) {
+    const bool all = g.ntaps * BNC <= 512 && g.ntaps <= kWgMaxGroupTaps;
+    hx = max_dx - min_dx;
+    hy = all ? max_dy - min_dy : 0;
+    for (int t = 0; t < g.ntaps; ++t) {
+      const ConvTap& tp = g.taps[t];
+      int gi = -1;
+      if (all) gi = ngroups ? 0 : -1;
+      else
+        for (int q = 0; q < ngroups; ++q)
+          if (p.groups[q].oy == tp.dy) gi = q;      // one group per filter row
+      if (gi < 0) {
+        gi = ngroups++;
+        p.groups[gi].oy = (int16_t)(all ? min_dy : tp.dy);
+        p.groups[gi].ox = (int16_t)min_dx;
+        p.groups[gi].map = 0;
+        p.groups[gi].ntaps = 0;
+      }
+      TapGroup& G = p.groups[gi];
+      if (G.ntaps >= kWgMaxGroupTaps || (G.ntaps + 1) * BNC > 512) return IDEAS_ERR_UNSUPPORTED;
+      G.drow[G.ntaps] = 0;   // filled below once the box is known
+      G.widx[G.ntaps] = (int16_t)t;   // index into g.taps, resolved below
+      ++G.ntaps;
     }
-    p.taps[t].oy = (int16_t)oy; p.taps[t].ox = (int16_t)ox; p.taps[t].widx = (int16_t)tp.widx;
-    p.taps[t].map = (int16_t)(py * 2 + px);
-    need[py * 2 + px] = true;
+    need[0] = true;
+  } else {
+    for (int t = 0; t < g.ntaps; ++t) {
+      const ConvTap& tp = g.taps[t];
+      int py = 0, px = 0, oy = tp.dy, ox = tp.dx;
+      if (g.i_s == 2) {
+        py = ((tp.dy % 2) + 2) % 2; px = ((tp.dx % 2) + 2) % 2;
+        oy = (tp.dy - py) / 2; ox = (tp.dx - px) / 2;
+      }
+      TapGroup& G = p.groups[ngroups++];
+      G.oy = (int16_t)oy; G.ox = (int16_t)ox; G.map = (int16_t)(py * 2 + px); G.ntaps = 1;
+      G.drow[0] = 0; G.widx[0] = (int16_t)tp.widx;
+      need[py * 2 + px] = true;
+    }
   }
+  choose_box32(g.N, g.QH, g.QW, hx, hy, reuse, &p.bw, &p.bh, &p.bn, &p.tiles_x, &p.tiles_y, &p.nboxes);
+  const int xbw = p.bw + hx, xbh = p.bh + hy;
+  if (reuse) {
+    for (int q = 0; q < ngroups; ++q) {
+      TapGroup& G = p.groups[q];
+      for (int j = 0; j < G.ntaps; ++j) {
+        const ConvTap& tp = g.taps[G.widx[j]];
+        G.drow[j] = (int16_t)((tp.dy - G.oy) * xbw + (tp.dx - G.ox));
+        G.widx[j] = (int16_t)tp.widx;
+      }
+    }
+  }
+  for (int k = 0; k < kWgPix / 8; ++k) {
+    const int q = k * 8;
+    const int xq = q % p.bw, yq = (q / p.bw) % p.bh, nq = q / (p.bw * p.bh);
+    p.rowbase[k] = (nq * xbh + yq) * xbw + xq;
+  }
+  p.x_group_bytes = (uint32_t)(p.bn * xbh * xbw) * 128u;
+  const uint32_t xbytes = (uint32_t)(BNC / 32) * p.x_group_bytes;
+  p.stage_bytes = (kWgABytes + xbytes + 1023u) & ~1023u;
+  p.stages = (int)(200 * 1024 / p.stage_bytes);
+  if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
+  if (p.stages < 2) return IDEAS_ERR_UNSUPPORTED;
+  int max_group = 1;
+  for (int q = 0; q < ngroups; ++q) max_group = p.groups[q].ntaps > max_group ? p.groups[q].ntaps : max_group;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(max_group * BNC)) cols <<= 1;
+  p.tmem_cols = cols;
   {
     const uint64_t dims[5] = {32, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N, (uint64_t)(g.OC / 32)};
     const uint64_t strides[4] = {(uint64_t)g.OC * 4, (uint64_t)g.OW * g.OC * 4, (uint64_t)g.OH * g.OW * g.OC * 4, 128};
@@ -929,7 +1037,7 @@ int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float
     if (wd < 1 || hd < 1) return IDEAS_ERR_UNSUPPORTED;
     const uint64_t dims[5] = {32, (uint64_t)wd, (uint64_t)hd, (uint64_t)g.N, (uint64_t)(g.IC / 32)};
     const uint64_t strides[4] = {(uint64_t)s * g.IC * 4, (uint64_t)s * g.IW * g.IC * 4, (uint64_t)g.IH * g.IW * g.IC * 4, 128};
-    const uint32_t box[5] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn, (uint32_t)(BNC / 32)};
+    const uint32_t box[5] = {32, (uint32_t)xbw, (uint32_t)xbh, (uint32_t)p.bn, (uint32_t)(BNC / 32)};
     int rc = encode_map(&p.x[m], x + ((int64_t)py * g.IW + px) * g.IC, 5, dims, strides, box,
                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
@@ -937,19 +1045,24 @@ int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float
   for (int m = 0; m < 4; ++m)
     if (!need[m]) p.x[m] = p.x[need[0] ? 0 : (need[1] ? 1 : (need[2] ? 2 : 3))];
 
-  const int base = ktiles * p.ctiles * g.ntaps;
+  const int base = ktiles * p.ctiles * ngroups;
   int splits = ceil_div(kNumSMs * 2, base);
   if (splits > p.nboxes) splits = p.nboxes;
   if (splits < 1) splits = 1;
   p.boxes_per_split = ceil_div(p.nboxes, splits);
   splits = ceil_div(p.nboxes, p.boxes_per_split);
-  dim3 grid(ktiles * p.ctiles, g.ntaps, splits);
-  switch (BNC) {
-    case 256: return launch_wgrad<256>(p, grid, st);
-    case 128: return launch_wgrad<128>(p, grid, st);
-    case 64: return launch_wgrad<64>(p, grid, st);
-    default: return launch_wgrad<32>(p, grid, st);
+  dim3 grid(ktiles * p.ctiles, ngroups, splits);
+  const uint32_t smem = p.stages * p.stage_bytes + 1024;
+  switch (max_group) {
+    case 1: return launch_wgrad<1>(p, grid, smem, st);
+    case 2: return launch_wgrad<2>(p, grid, smem, st);
+    case 3: return launch_wgrad<3>(p, grid, smem, st);
+    case 4: return launch_wgrad<4>(p, grid, smem, st);
+    case 9: return launch_wgrad<9>(p, grid, smem, st);
+    default: break;
   }
+  set_error("conv_umma_wgrad: unsupported tap group size %d", max_group);
+  return IDEAS_ERR_UNSUPPORTED;
 }
 
 }  // namespace ideas
@@ -959,6 +1072,10 @@ extern "C" int ideas_umma_available(void) { return 1; }
 extern "C" int ideas_set_option(const char* name, int value) {
   if (name && !strcmp(name, "tma_tf32")) {
     ideas::g_tma_tf32.store(value ? 1 : 0);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "wgrad_reuse")) {
+    ideas::g_wgrad_reuse.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "halo")) {

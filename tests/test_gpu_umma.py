@@ -137,6 +137,11 @@ WGRAD_CASES = [
     (4, 384, 384, 8, 8, 3, 1, 1),
     (2, 96, 64, 20, 12, 3, 1, 1),
     (2, 128, 64, 33, 33, 3, 2, 0),
+    (1, 32, 64, 256, 256, 3, 1, 1),        # 9-tap group (C = 32), 32x1 boxes
+    (2, 128, 128, 130, 34, 3, 1, 0),       # filter-row groups, ragged boxes, pad 0
+    (3, 64, 160, 21, 45, 3, 1, 1),         # odd sizes, K = 160
+    (5, 256, 128, 9, 9, 3, 1, 1),          # 8x4 boxes hanging over 9x9 maps
+    (2, 768, 384, 17, 17, 2, 1, 0),          # 2x2 valid conv
 ]
 
 

@@ -302,6 +302,240 @@ __global__ void __launch_bounds__(128) blur4_nhwc_kernel(float* __restrict__ out
   else blur4sep_strip<XT, EPI, false>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// resampling fast paths (separable taps, <= 4x4, NHWC, minor % 4 == 0):
+//   down = 2: the skip branch of a down-sampling ResBlock is Blur -> 1x1 stride-2 conv (reference
+//     models.py:68-74,213-227); only every other blurred pixel is ever read, so the host side runs
+//     upfirdn2d(down = 2) -> 1x1 stride-1 conv instead (identical arithmetic): the blur writes a quarter
+//     of the pixels and the conv reads a quarter.
+//   up = 2: its adjoint, and the forward of the up-sampling skip (1x1 transposed conv stride 2 -> Blur
+//     == 1x1 conv at low resolution -> upfirdn2d(up = 2), models.py:78-95): each output pixel meets only
+//     the 2x2 taps whose parity matches the zero-inserted grid, and the zeros are never materialised.
+// Both keep the thread mapping of the blur kernel (4 channels x a few columns, sliding down a strip).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool taps_separable(const float* __restrict__ kernel, const UpfirdnParams& p, float (&rowk)[4],
+                                               float (&colk)[4]) {
+  Taps4 tp;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      tp.k[a][b] = (a < p.kh && b < p.kw) ? __ldg(kernel + (p.kh - 1 - a) * p.kw + (p.kw - 1 - b)) : 0.f;
+  bool sep = tp.k[0][0] != 0.f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) sep = sep && (tp.k[a][b] * tp.k[0][0] == tp.k[a][0] * tp.k[0][b]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    rowk[i] = tp.k[0][i];
+    colk[i] = tp.k[i][0] / tp.k[0][0];
+  }
+  return sep;
+}
+
+// direct form for one (pixel, 4 channels): used only when the taps are not rank 1
+__device__ float4 upfirdn_direct4(const float* __restrict__ x, const float* __restrict__ kernel, const UpfirdnParams& p, int m,
+                                  int oy, int ox, int c) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ky = 0; ky < p.kh; ++ky) {
+    const int uy = oy * p.down_y + ky - p.pad_y0;
+    if (uy < 0 || uy % p.up_y) continue;
+    const int iy = uy / p.up_y;
+    if (iy >= p.in_h) continue;
+    for (int kx = 0; kx < p.kw; ++kx) {
+      const int ux = ox * p.down_x + kx - p.pad_x0;
+      if (ux < 0 || ux % p.up_x) continue;
+      const int ix = ux / p.up_x;
+      if (ix >= p.in_w) continue;
+      const float w = __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)m * p.in_h + iy) * p.in_w + ix) * p.minor + c));
+      v.x = fmaf(a.x, w, v.x); v.y = fmaf(a.y, w, v.y); v.z = fmaf(a.z, w, v.z); v.w = fmaf(a.w, w, v.w);
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ f2x2 ldg_f2x2_guard(const float* p, bool ok) {
+  return ok ? ldg_f2x2(p) : f2x2{0ull, 0ull};
+}
+__device__ __forceinline__ void st_f2x2(float* p, const f2x2& v) {
+  float4 o;
+  unpack2(v.lo, o.x, o.y);
+  unpack2(v.hi, o.z, o.w);
+  st_stream4(p, o);
+}
+
+// out[oy][ox] = sum_{ky,kx} k[ky][kx] * in[2*oy + ky - pad_y0][2*ox + kx - pad_x0]
+template <int ROWS, int XT>
+__global__ void __launch_bounds__(128) blur4_down2_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                          const float* __restrict__ kernel, UpfirdnParams p) {
+  float rowk[4], colk[4];
+  const bool sep = taps_separable(kernel, p, rowk, colk);
+  const int c4n = p.minor >> 2;
+  const int groups = (p.out_w + XT - 1) / XT;
+  const int lin = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lin >= groups * c4n) return;
+  const int og = lin / c4n;
+  const int c = (lin - og * c4n) << 2;
+  const int ox0 = og * XT;
+  const int m = blockIdx.z;
+  const int oy0 = blockIdx.y * ROWS;
+  const int oy1 = min(oy0 + ROWS, p.out_h);
+  float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
+  const int64_t orow = (int64_t)p.out_w * p.minor;
+  if (!sep) {
+    for (int oy = oy0; oy < oy1; ++oy)
+      for (int j = 0; j < XT && ox0 + j < p.out_w; ++j)
+        st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, upfirdn_direct4(x, kernel, p, m, oy, ox0 + j, c));
+    return;
+  }
+  unsigned long long kx[4], ky[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    kx[i] = pack2(rowk[i], rowk[i]);
+    ky[i] = pack2(colk[i], colk[i]);
+  }
+  constexpr int NL = 2 * XT + 2;          // input columns feeding XT outputs
+  const int ix0 = 2 * ox0 - p.pad_x0;
+  bool colok[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) colok[i] = (ix0 + i) >= 0 && (ix0 + i) < p.in_w;
+  const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
+  const int64_t irow = (int64_t)p.in_w * p.minor;
+  f2x2 w[4][XT];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int j = 0; j < XT; ++j) w[s][j] = f2x2{0ull, 0ull};
+  const int iy_begin = 2 * oy0 - p.pad_y0;
+  const int iy_end = 2 * (oy1 - 1) - p.pad_y0 + 3;
+  const float* rp = xin + (int64_t)iy_begin * irow + (int64_t)ix0 * p.minor;
+  float* op = o + (int64_t)oy0 * orow;
+  for (int iy = iy_begin; iy <= iy_end; iy += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (iy + u <= iy_end) {
+        const bool rowok = (iy + u) >= 0 && (iy + u) < p.in_h;
+        f2x2 r[NL];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) r[i] = ldg_f2x2_guard(rp + (int64_t)i * p.minor, rowok && colok[i]);
+        // relative row (iy + u - iy_begin) is odd and >= 3  <=>  an output row completes here
+        const bool emit = (u & 1) && (iy + u - iy_begin) >= 3;
+#pragma unroll
+        for (int j = 0; j < XT; ++j) {
+          f2x2 a;
+          a.lo = fma2(r[2 * j + 3].lo, kx[3], fma2(r[2 * j + 2].lo, kx[2], fma2(r[2 * j + 1].lo, kx[1], mul2(r[2 * j].lo, kx[0]))));
+          a.hi = fma2(r[2 * j + 3].hi, kx[3], fma2(r[2 * j + 2].hi, kx[2], fma2(r[2 * j + 1].hi, kx[1], mul2(r[2 * j].hi, kx[0]))));
+          w[u][j] = a;
+          if (emit && ox0 + j < p.out_w) {
+            const f2x2& w0 = w[(u + 1) & 3][j];
+            const f2x2& w1 = w[(u + 2) & 3][j];
+            const f2x2& w2 = w[(u + 3) & 3][j];
+            f2x2 d;
+            d.lo = fma2(a.lo, ky[3], fma2(w2.lo, ky[2], fma2(w1.lo, ky[1], mul2(w0.lo, ky[0]))));
+            d.hi = fma2(a.hi, ky[3], fma2(w2.hi, ky[2], fma2(w1.hi, ky[1], mul2(w0.hi, ky[0]))));
+            st_f2x2(op + (int64_t)j * p.minor, d);
+          }
+        }
+        rp += irow;
+        if (emit) op += orow;
+      }
+    }
+  }
+}
+
+// out[oy][ox] = sum_{ky,kx} k[ky][kx] * z[oy + ky - pad_y0][ox + kx - pad_x0],  z[2i][2j] = in[i][j], 0 elsewhere.
+// With s = ox - pad_x0: the two live taps are kx = (s & 1), (s & 1) + 2 and meet in[ja], in[ja + 1], ja = (s + 1) >> 1
+// (same along y).  PX = parity of pad_x0 (compile time, so the per-thread register arrays are indexed statically).
+template <int ROWS, int XT, int PX>
+__global__ void __launch_bounds__(128) blur4_up2_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                        const float* __restrict__ kernel, UpfirdnParams p) {
+  float rowk[4], colk[4];
+  const bool sep = taps_separable(kernel, p, rowk, colk);
+  constexpr int NO = 2 * XT;              // output columns per thread
+  const int c4n = p.minor >> 2;
+  const int groups = (p.out_w + NO - 1) / NO;
+  const int lin = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lin >= groups * c4n) return;
+  const int og = lin / c4n;
+  const int c = (lin - og * c4n) << 2;
+  const int ox0 = og * NO;
+  const int m = blockIdx.z;
+  const int oy0 = blockIdx.y * ROWS;
+  const int oy1 = min(oy0 + ROWS, p.out_h);
+  float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
+  const int64_t orow = (int64_t)p.out_w * p.minor;
+  if (!sep) {
+    for (int oy = oy0; oy < oy1; ++oy)
+      for (int j = 0; j < NO && ox0 + j < p.out_w; ++j)
+        st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, upfirdn_direct4(x, kernel, p, m, oy, ox0 + j, c));
+    return;
+  }
+  unsigned long long kx[4], ky[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    kx[i] = pack2(rowk[i], rowk[i]);
+    ky[i] = pack2(colk[i], colk[i]);
+  }
+  // columns: s0 = ox0 - pad_x0 has parity PX (ox0 is even); first input column ja0 = (s0 + 1) >> 1
+  const int s0 = ox0 - p.pad_x0;
+  const int ja0 = (s0 + 1) >> 1;
+  constexpr int NL = XT + 2;
+  bool colok[NL];
+#pragma unroll
+  for (int i = 0; i < NL; ++i) colok[i] = (ja0 + i) >= 0 && (ja0 + i) < p.in_w;
+  const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
+  const int64_t irow = (int64_t)p.in_w * p.minor;
+  // rows: output row oy (t = oy - pad_y0) meets input rows ia, ia + 1 with ia = (t + 1) >> 1 and taps (t & 1), (t & 1) + 2
+  const int ia_begin = (oy0 - p.pad_y0 + 1) >> 1;
+  const int ia_end = ((oy1 - 1 - p.pad_y0 + 1) >> 1) + 1;
+  f2x2 hprev[NO], hcur[NO];
+#pragma unroll
+  for (int j = 0; j < NO; ++j) hprev[j] = hcur[j] = f2x2{0ull, 0ull};
+  const float* rp = xin + (int64_t)ia_begin * irow + (int64_t)ja0 * p.minor;
+  for (int ia = ia_begin; ia <= ia_end; ++ia) {
+    const bool rowok = ia >= 0 && ia < p.in_h;
+    f2x2 r[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) r[i] = ldg_f2x2_guard(rp + (int64_t)i * p.minor, rowok && colok[i]);
+#pragma unroll
+    for (int j = 0; j < NO; ++j) {
+      // s = s0 + j: parity (PX + j) & 1; input offset ((s + 1) >> 1) - ja0
+      const int par = (PX + j) & 1;
+      const int off = PX ? j / 2 : j / 2 + (j & 1);   // ((s0 + j + 1) >> 1) - ((s0 + 1) >> 1)
+      hcur[j].lo = fma2(r[off + 1].lo, kx[par + 2], mul2(r[off].lo, kx[par]));
+      hcur[j].hi = fma2(r[off + 1].hi, kx[par + 2], mul2(r[off].hi, kx[par]));
+    }
+    // rows (ia - 1, ia) feed output rows t = 2*(ia - 1) - 1 + ... : t with (t + 1) >> 1 == ia - 1  ->  t = 2*ia - 3, 2*ia - 2
+    if (ia > ia_begin) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int t = 2 * ia - 3 + q;
+        const int oy = t + p.pad_y0;
+        if (oy >= oy0 && oy < oy1) {
+          const int par = t & 1;
+          const unsigned long long k0 = par ? ky[1] : ky[0], k2 = par ? ky[3] : ky[2];
+          float* op = o + (int64_t)oy * orow;
+#pragma unroll
+          for (int j = 0; j < NO; ++j) {
+            if (ox0 + j < p.out_w) {
+              f2x2 d;
+              d.lo = fma2(hcur[j].lo, k2, mul2(hprev[j].lo, k0));
+              d.hi = fma2(hcur[j].hi, k2, mul2(hprev[j].hi, k0));
+              st_f2x2(op + (int64_t)j * p.minor, d);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NO; ++j) hprev[j] = hcur[j];
+    rp += irow;
+  }
+}
+
 }  // namespace ideas
 
 using namespace ideas;
@@ -338,6 +572,23 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
     if (bias) blur4_nhwc_kernel<ROWS, XT, true><<<grid, 128, 0, st>>>(out, x, kernel, bias, p);
     else blur4_nhwc_kernel<ROWS, XT, false><<<grid, 128, 0, st>>>(out, x, kernel, bias, p);
     IDEAS_CHECK_LAUNCH("upfirdn2d(fast)");
+    return IDEAS_OK;
+  }
+  const bool resample_ok = kernel_h <= 4 && kernel_w <= 4 && minor % 4 == 0 && aligned16(out) && aligned16(x) && !bias &&
+                           major <= 65535;
+  if (resample_ok && up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2) {
+    constexpr int ROWS = 16, XT = 2;
+    dim3 grid(ceil_div(ceil_div(p.out_w, XT) * (minor / 4), 128), ceil_div(p.out_h, ROWS), major);
+    blur4_down2_kernel<ROWS, XT><<<grid, 128, 0, st>>>(out, x, kernel, p);
+    IDEAS_CHECK_LAUNCH("upfirdn2d(down2)");
+    return IDEAS_OK;
+  }
+  if (resample_ok && up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1) {
+    constexpr int ROWS = 32, XT = 2;
+    dim3 grid(ceil_div(ceil_div(p.out_w, 2 * XT) * (minor / 4), 128), ceil_div(p.out_h, ROWS), major);
+    if (pad_x0 & 1) blur4_up2_kernel<ROWS, XT, 1><<<grid, 128, 0, st>>>(out, x, kernel, p);
+    else blur4_up2_kernel<ROWS, XT, 0><<<grid, 128, 0, st>>>(out, x, kernel, p);
+    IDEAS_CHECK_LAUNCH("upfirdn2d(up2)");
     return IDEAS_OK;
   }
   int64_t blocks = ceil_div64(total, 256);

@@ -20,7 +20,7 @@ from torch import nn
 
 from .stylegan2.model import (Blur, EqualConv2d, EqualLinear, ScaledLeakyReLU,
                               StyledConv_without_noise as StyledConv)
-from .stylegan2.op import FusedLeakyReLU
+from .stylegan2.op import FusedLeakyReLU, upfirdn2d
 from .stylegan2.op import conv as _ops
 from .stylegan2.op.conv import PackWeight
 from .stylegan2.op.elementwise import add_scale
@@ -39,11 +39,12 @@ class EqualConvTranspose2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
-    def forward(self, input):
+    def forward(self, input, stride=None):
         cin, cout, k, _ = self.weight.shape
+        stride = self.stride if stride is None else stride
         # (in, out, k, k) is the OIHW weight of the stride-s conv whose adjoint this layer is
         wp = PackWeight.apply(self.weight, False, self.scale)
-        out = _ops.conv_transpose2d(input, wp, C_out=cout, kh=k, kw=k, stride=self.stride, pad=self.padding)
+        out = _ops.conv_transpose2d(input, wp, C_out=cout, kh=k, kw=k, stride=stride, pad=self.padding)
         if self.bias is not None:
             out = out + self.bias.view(1, -1, 1, 1)
         return out
@@ -109,6 +110,19 @@ class ConvLayer(nn.Sequential):
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if isinstance(m, EqualConv2d) and isinstance(nxt, FusedLeakyReLU):
                 out = m(out, activation=nxt)          # one kernel: conv + bias + leaky ReLU
+                i += 2
+            elif (isinstance(m, Blur) and isinstance(nxt, EqualConv2d) and nxt.weight.shape[2] == 1
+                  and nxt.stride == 2 and nxt.padding == 0):
+                # Blur -> 1x1 stride-2 conv (down-sampling skip): the conv reads every other blurred pixel, so
+                # blur and decimate in one pass (upfirdn2d down=2) and run the 1x1 conv at the low resolution
+                out = nxt(upfirdn2d(out, m.kernel, down=2, pad=m.pad), stride=1)
+                i += 2
+            elif (isinstance(m, EqualConvTranspose2d) and isinstance(nxt, Blur) and m.weight.shape[2] == 1
+                  and m.stride == 2 and m.padding == 0 and m.bias is None):
+                # 1x1 stride-2 transposed conv -> Blur (up-sampling skip): a bias-free 1x1 conv commutes with zero
+                # insertion, so convolve at the low resolution and let upfirdn2d(up=2) interleave the zeros on the
+                # fly (its trailing zero replaces one unit of right padding)
+                out = upfirdn2d(m(out, stride=1), nxt.kernel, up=2, pad=(nxt.pad[0], nxt.pad[1] - 1))
                 i += 2
             else:
                 out = m(out)

@@ -88,16 +88,18 @@ class EqualConv2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
-    def forward(self, input, activation: FusedLeakyReLU | None = None):
-        """``activation``: a FusedLeakyReLU module to fuse into the conv epilogue."""
+    def forward(self, input, activation: FusedLeakyReLU | None = None, stride: int | None = None):
+        """``activation``: a FusedLeakyReLU module to fuse into the conv epilogue.  ``stride`` overrides the
+        module's stride (ConvLayer folds the decimation of a 1x1 stride-2 conv into the preceding blur)."""
         k = self.weight.shape[2]
+        stride = self.stride if stride is None else stride
         wp = PackWeight.apply(self.weight, False, self.scale)
         if activation is not None:
             if self.bias is not None:
                 raise RuntimeError("EqualConv2d: a fused activation brings its own bias")
-            return _ops.conv2d(input, wp, activation.bias, K=self.weight.shape[0], kh=k, kw=k, stride=self.stride,
+            return _ops.conv2d(input, wp, activation.bias, K=self.weight.shape[0], kh=k, kw=k, stride=stride,
                                pad=self.padding, act=True, alpha=activation.negative_slope, gain=activation.scale)
-        return _ops.conv2d(input, wp, self.bias, K=self.weight.shape[0], kh=k, kw=k, stride=self.stride,
+        return _ops.conv2d(input, wp, self.bias, K=self.weight.shape[0], kh=k, kw=k, stride=stride,
                            pad=self.padding)
 
     def __repr__(self):

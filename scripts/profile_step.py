@@ -19,4 +19,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     tr.step(X, 3)
     tr.step(X, 4)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+rows = [e for e in prof.key_averages() if e.self_device_time_total > 0]
+rows.sort(key=lambda e: -e.self_device_time_total)
+total = sum(e.self_device_time_total for e in rows)
+print(f"total device time {total / 1e3:.1f} ms for 2 steps")
+for e in rows[:70]:
+    print(f"{e.self_device_time_total / 1e3:9.2f} ms {100 * e.self_device_time_total / total:5.1f}% {e.count:6d} x {e.self_device_time_total / max(e.count, 1):8.1f} us  {e.key[:110]}")

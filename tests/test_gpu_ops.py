@@ -128,6 +128,40 @@ def test_blur_fwd_bwd_double_bwd(op, C, H, W, pad, gain):
         assert rel(a, b) <= 5e-6
 
 
+@pytest.mark.parametrize("C,H,W,up,down,pad", [
+    (8, 16, 16, 1, 2, (1, 1)), (64, 255, 255, 1, 2, (1, 1)), (12, 33, 20, 1, 2, (2, 1)), (4, 9, 31, 1, 2, (0, 0)),
+    (128, 64, 64, 1, 2, (2, 2)), (8, 16, 16, 2, 1, (2, 1)), (64, 64, 64, 2, 1, (2, 1)), (12, 17, 9, 2, 1, (1, 1)),
+    (4, 5, 31, 2, 1, (3, 2)), (32, 31, 33, 2, 1, (2, 2)), (3, 12, 12, 2, 1, (2, 1)), (6, 12, 12, 1, 2, (1, 1))])
+def test_resampling_fast_paths_fwd_bwd_double_bwd(op, C, H, W, up, down, pad):
+    """upfirdn2d with up = 2 or down = 2 (the fused skip-branch kernels; C % 4 != 0 exercises the generic kernel)
+    against the oracle restatement of upfirdn2d_native (upfirdn2d.py:159-200), forward, backward (which runs the
+    opposite resampling kernel) and double backward."""
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn(2, C, H, W, generator=g)
+    k = O.make_kernel([1, 3, 3, 1]) * (up ** 2)
+
+    def run(fn, dev):
+        xx = x.to(dev).requires_grad_(True)
+        out = fn(xx, k.to(dev), up=up, down=down, pad=pad)
+        gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(16)).to(dev).requires_grad_(True)
+        (gx,) = torch.autograd.grad(out, xx, gy, create_graph=True)
+        (ggy,) = torch.autograd.grad(gx.pow(2).sum(), gy)
+        return out, gx, ggy
+
+    for a, b in zip(run(op.upfirdn2d, "cuda"), run(O.upfirdn2d, "cpu")):
+        assert a.shape == b.shape
+        assert rel(a, b) <= 5e-6
+
+
+def test_resampling_non_separable_taps(op):
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(2, 8, 13, 11, generator=g)
+    k = torch.randn(4, 4, generator=g)
+    for up, down, pad in ((1, 2, (1, 1)), (2, 1, (2, 1))):
+        got = op.upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad)
+        assert rel(got, O.upfirdn2d(x, k, up=up, down=down, pad=pad)) <= 5e-6
+
+
 def test_blur_bias_act_fused_epilogue(op):
     g = torch.Generator().manual_seed(7)
     x, b = torch.randn(2, 16, 12, 12, generator=g), torch.randn(16, generator=g)

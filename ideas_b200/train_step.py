@@ -77,10 +77,15 @@ class Trainer:
     """The ``trainer`` dict of train.py:390-432 as an object (``trainer[key]`` still works)."""
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
-                 states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False):
+                 states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None):
         self.args = args
         self.device = torch.device(device)
         self.cuda_graphs = bool(cuda_graphs and self.device.type == "cuda")
+        # independent sub-graphs of one iteration (Dreal on the real batch, the co-occurrence branch, the
+        # E(container)->Ex branch) run on side streams: their HBM-bound kernels overlap the tensor-bound ones of
+        # the main branch, and autograd replays the same streams in backward.  Same arithmetic, same results.
+        self.multi_stream = bool((self.cuda_graphs if multi_stream is None else multi_stream) and self.device.type == "cuda")
+        self._side_streams: List[torch.cuda.Stream] = []
         self._graphs: Dict[tuple, tuple] = {}
         self.replayed_launches = 0        # library kernels launched through graph replays (see bench.py gpu_launches)
         self._pool = None
@@ -138,10 +143,11 @@ class Trainer:
                 off += p.numel()
 
     # -------------------------------------------------------------------------------------
-    def _rand_like_Z(self, S, draws, key, device_rng=False):
+    def _rand_like_Z(self, X, draws, key, device_rng=False):
+        """Z ~ U(-1,1) of shape (B, N, H/16, W/16) (train.py:60-61: the structure code of E is 1/16 resolution)."""
         if draws is not None and key in draws:
             return draws[key].to(self.device)
-        shape = (S.shape[0], self.args.N, S.shape[2], S.shape[3])
+        shape = (X.shape[0], self.args.N, X.shape[2] // 16, X.shape[3] // 16)
         if device_rng:                     # CUDA-graph path: Philox on the device (no H2D copy inside the graph)
             return torch.rand(shape, dtype=torch.float, device=self.device) * 2 - 1
         # train.py:60-61 draws on the CPU generator and copies; kept so seeded runs match the reference
@@ -151,6 +157,30 @@ class Trainer:
         if draws is not None and key in draws:
             return draws[key].to(self.device)
         return torch.rand_like(T) * 2 - 1
+
+    # ------------------------------------------------------------------------------------- side streams
+    def _fork(self, idx: int, *inputs):
+        """Context manager: run the body on side stream ``idx`` after everything enqueued so far on the current
+        stream.  ``inputs`` are tensors produced on the current stream that the body reads."""
+        import contextlib
+        if not self.multi_stream:
+            return contextlib.nullcontext()
+        while len(self._side_streams) <= idx:
+            self._side_streams.append(torch.cuda.Stream(device=self.device))
+        side = self._side_streams[idx]
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        for t in inputs:
+            t.record_stream(side)
+        return torch.cuda.stream(side)
+
+    def _join(self, idx: int, *outputs):
+        """Make the current stream wait for side stream ``idx``; ``outputs`` were produced there."""
+        if not self.multi_stream:
+            return
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(self._side_streams[idx])
+        for t in outputs:
+            t.record_stream(main)
 
     # box sets one iteration needs: name -> number of crops (train.py:80-82,168-169)
     def _box_specs(self):
@@ -234,19 +264,29 @@ class Trainer:
             requires_grad(t[k], False)
         for k in ("Dreal", "Dco", "Ddist"):
             requires_grad(t[k], True)
+        # host-side draws in the reference's order (train.py:60-61 then :80-82) before any branch uses them
+        Z = self._rand_like_Z(X, draws, "Z_d", device_rng)
+        fake_boxes = crops("fake_crops_d", a.n_crop)
+        real_boxes = crops("real_crops_d", a.n_crop)
+        ref_boxes = crops("ref_crops_d", a.ref_crop * a.n_crop)
+        with self._fork(0, X):                                   # Dreal on the real batch needs nothing from E / G
+            real_pred = t["Dreal"](X)
+        with self._fork(1, X):                                   # so do the real / reference patches of Dco
+            real_patch = patchify_image(X, a.n_crop, crops=real_boxes)
+            ref_patch = patchify_image(X, a.ref_crop * a.n_crop, crops=ref_boxes)
+            # train.py:85-86 evaluates the fake patches first and reuses ref_input for the real ones; ref_input
+            # does not depend on the first argument, so the order of the two calls is immaterial
+            real_texture_pred, ref_input = t["Dco"](real_patch, ref_patch, ref_batch=a.ref_crop)
         S1, T1 = t["E"](X)
-        Z = self._rand_like_Z(S1, draws, "Z_d", device_rng)
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_d")
         hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
         fake_pred = t["Dreal"](torch.cat((hat_X1, hat_X2, hat_X3), 0))
-        real_pred = t["Dreal"](X)
+        fake_patch = patchify_image(hat_X2, a.n_crop, crops=fake_boxes)
+        self._join(1, real_texture_pred, ref_input, real_patch, ref_patch)
+        fake_texture_pred, _ = t["Dco"](fake_patch, ref_input=ref_input)
+        self._join(0, real_pred)
         D_real_loss = d_logistic_loss(real_pred, fake_pred)
-        fake_patch = patchify_image(hat_X2, a.n_crop, crops=crops("fake_crops_d", a.n_crop))
-        real_patch = patchify_image(X, a.n_crop, crops=crops("real_crops_d", a.n_crop))
-        ref_patch = patchify_image(X, a.ref_crop * a.n_crop, crops=crops("ref_crops_d", a.ref_crop * a.n_crop))
-        fake_texture_pred, ref_input = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
-        real_texture_pred, _ = t["Dco"](real_patch, ref_input=ref_input)
         D_texture_loss = d_logistic_loss(real_texture_pred, fake_texture_pred)
         D_dist_loss = d_logistic_loss(t["Ddist"](T2), t["Ddist"](T1))
         loss.update(D_real_loss=D_real_loss, D_texture_loss=D_texture_loss, D_dist_loss=D_dist_loss)
@@ -275,21 +315,27 @@ class Trainer:
         for k in ("Dreal", "Dco", "Ddist"):
             requires_grad(t[k], False)
         S1, T1 = t["E"](X)
-        Z = self._rand_like_Z(S1, draws, "Z_g", device_rng)
+        Z = self._rand_like_Z(X, draws, "Z_g", device_rng)
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_g")
         hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
+        fake_boxes = crops("fake_crops_g", a.n_crop)
+        ref_boxes = crops("ref_crops_g", a.ref_crop * a.n_crop)
+        container = hat_X3 if late else hat_X2
+        with self._fork(0, container, S2, Z):                    # E(container) -> Ex branch (train.py:178-189)
+            hat_S2, _ = t["E"](container)
+            E_stru_loss = F.l1_loss(hat_S2, S2)
+            Ex_loss = F.l1_loss(t["Ex"](hat_S2), Z)
+        with self._fork(1, hat_X2, X):                           # co-occurrence branch (train.py:168-175)
+            fake_patch = patchify_image(hat_X2, a.n_crop, crops=fake_boxes)
+            ref_patch = patchify_image(X, a.ref_crop * a.n_crop, crops=ref_boxes)
+            fake_patch_pred, _ = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
+            G_texture_loss = g_nonsaturating_loss(fake_patch_pred)
         G_rec_loss = F.l1_loss(hat_X1, X)
         G_real_loss = g_nonsaturating_loss(t["Dreal"](torch.cat((hat_X1, hat_X2, hat_X3), 0)))
         E_dist_loss = g_nonsaturating_loss(t["Ddist"](T1))
-        fake_patch = patchify_image(hat_X2, a.n_crop, crops=crops("fake_crops_g", a.n_crop))
-        ref_patch = patchify_image(X, a.ref_crop * a.n_crop, crops=crops("ref_crops_g", a.ref_crop * a.n_crop))
-        fake_patch_pred, _ = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
-        G_texture_loss = g_nonsaturating_loss(fake_patch_pred)
-        container = hat_X3 if late else hat_X2
-        hat_S2, _ = t["E"](container)
-        E_stru_loss = F.l1_loss(hat_S2, S2)
-        Ex_loss = F.l1_loss(t["Ex"](hat_S2), Z)
+        self._join(0, E_stru_loss, Ex_loss)
+        self._join(1, G_texture_loss)
         Loss_total = (G_rec_loss + G_texture_loss + 2 * G_real_loss) + (E_dist_loss + E_stru_loss) + a.lambda_Ex * Ex_loss
         self.g_optim.zero_grad()
         Loss_total.backward(retain_graph=True)

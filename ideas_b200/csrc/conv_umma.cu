@@ -1045,8 +1045,11 @@ int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* x, const float
   for (int m = 0; m < 4; ++m)
     if (!need[m]) p.x[m] = p.x[need[0] ? 0 : (need[1] ? 1 : (need[2] ? 2 : 3))];
 
+  // one CTA per SM (200 KB of shared memory each): size the pixel splits so the grid is ONE wave that fills
+  // the 148 SMs without spilling into a second, nearly empty one (ncu on the 128->128 @256^2 shape: a grid of
+  // 297 CTAs left the SMs idle a third of the time)
   const int base = ktiles * p.ctiles * ngroups;
-  int splits = ceil_div(kNumSMs * 2, base);
+  int splits = kNumSMs / base;
   if (splits > p.nboxes) splits = p.nboxes;
   if (splits < 1) splits = 1;
   p.boxes_per_split = ceil_div(p.nboxes, splits);

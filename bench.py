@@ -194,13 +194,45 @@ def roofline_sections(peaks, peak_kind):
     out["roofline"] = {
         "kernel": "conv_igemm (modulated 3x3 conv fwd, 16x512x64x64 -> 512, demod+bias+lrelu fused)",
         "bound": "tensor", "achieved": flops / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-        "frac": flops / t / 1e12 / tf32_peak, "traffic": None,
+        "frac": flops / t / 1e12 / tf32_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1b_conv_fwd_cfg3.raw.csv);
+        # algorithmic bytes are 277 MB (x 134 + y 134 + packed weights 9.4): weights and part of x are L2 hits
+        "traffic": 163231488 + 83914752,
         "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops {peaks['bf16_tflops']} x 0.5 (kind::tf32 issues at half the bf16 rate)",
         "frac_of_bf16_peak": flops / t / 1e12 / peaks["bf16_tflops"],
         "path": "tcgen05 kind::tf32" if umma else "fp32 FFMA (SIMT)", "algorithmic_flops_per_launch": flops,
         "ms_per_launch": t * 1e3,
     }
-    del x, y
+    # --- cfg-3 weight gradient (same shape)
+    dy = torch.randn(N, H, H, K, device=dev)
+    dwp = torch.zeros(9, K, C, device=dev)
+
+    def wgrad():
+        _lib.call("ideas_conv2d_wgrad", ptr(dwp), ptr(x), ptr(dy), ptr(None), ptr(None), N, H, H, C, K, 3, 3, 1, 1, H, H, impl,
+                  stream_ptr(x))
+
+    t = time_kernel(wgrad, iters=10, warm=2)
+    out["roofline_wgrad"] = {"kernel": "conv_umma_wgrad (cfg-3 shape, 16x512x64x64, 512->512)", "bound": "tensor",
+                             "achieved": flops / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                             "frac": flops / t / 1e12 / tf32_peak, "traffic": None, "ms_per_launch": t * 1e3}
+    del x, y, dy
+    # --- halo-reuse kernel on the widest low-channel layer of G / Dreal: 128 -> 128 at 256x256, batch 32
+    N2, C2, H2 = 32, 128, 256
+    x2 = torch.randn(N2, H2, H2, C2, device=dev)
+    w2 = torch.randn(9, C2, C2, device=dev) / (C2 * 9) ** 0.5
+    y2 = torch.empty(N2, H2, H2, C2, device=dev)
+
+    def conv2():
+        _lib.call("ideas_conv2d_forward", ptr(y2), ptr(x2), ptr(w2), ptr(None), ptr(None), ptr(bias[:C2]), N2, H2, H2, C2, C2, 3, 3,
+                  1, 1, _lib.ACT_LRELU, 0.2, 2 ** 0.5, impl, stream_ptr(x2))
+
+    t = time_kernel(conv2, iters=10, warm=2)
+    f2 = 2.0 * N2 * H2 * H2 * C2 * C2 * 9
+    out["roofline_halo"] = {"kernel": "conv_umma_halo (3x3 conv fwd, 32x128x256x256 -> 128, bias+lrelu fused)", "bound": "tensor",
+                            "achieved": f2 / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": f2 / t / 1e12 / tf32_peak,
+                            # ncu --set full, profiles/r1b_conv_halo_g256.raw.csv; algorithmic 2.148 GB
+                            "traffic": 1076674000 + 1030189000, "ms_per_launch": t * 1e3}
+    del x2, y2
     # --- cfg 2: Blur pad (2,2), (32,128,256,256) -> (32,128,257,257)
     B, Cb, Hb = 32, 128, 256
     xb = torch.randn(B, Hb, Hb, Cb, device=dev)
@@ -218,7 +250,8 @@ def roofline_sections(peaks, peak_kind):
     out["roofline_hbm"] = {
         "kernel": "blur4_nhwc (upfirdn2d up=down=1, 4x4, pad (2,2), 32x128x256x256)", "bound": "hbm",
         "achieved": nbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / t / 1e9 / peaks["hbm_gbs"],
-        "traffic": None, "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs", "algorithmic_bytes_per_launch": nbytes,
+        "traffic": 1173469000 + 1033594000,    # ncu --set full, profiles/r1b_blur.raw.csv
+        "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs", "algorithmic_bytes_per_launch": nbytes,
         "ms_per_launch": t * 1e3,
     }
     return out

@@ -64,7 +64,30 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(float* __restric
 // ---------------------------------------------------------------------------------------
 // fast path: up = down = 1, kernel <= 4x4, minor % 4 == 0 (NHWC)
 // ---------------------------------------------------------------------------------------
-struct Taps4 { float k[4][4]; };  // already flipped and zero-extended: k[ky][kx] meets in[oy+ky-pad][ox+kx-pad]
+struct Taps4 { float k[4][4]; };
+
+// Output epilogues of the blur kernels:
+//   EPI 0: none
+//   EPI 1: (v + bias[c]) -> lrelu(alpha) -> * gain                      (Blur -> FusedLeakyReLU, forward)
+//   EPI 2: v * (ref > 0 ? 1 : alpha) * gain, per-thread channel sums    (backward of act -> Blur: the blurred
+//          gradient meets the mask of the activation that fed the blur; the sums are the bias gradient)
+template <int EPI>
+__device__ __forceinline__ void blur_epilogue(float4& v, const float4& b4, const UpfirdnParams& p, const float* ref,
+                                              int64_t off, float4& bsum) {
+  if (EPI == 1) {
+    v.x = lrelu(v.x + b4.x, p.alpha) * p.gain;
+    v.y = lrelu(v.y + b4.y, p.alpha) * p.gain;
+    v.z = lrelu(v.z + b4.z, p.alpha) * p.gain;
+    v.w = lrelu(v.w + b4.w, p.alpha) * p.gain;
+  } else if (EPI == 2) {
+    const float4 r = ld_stream4(ref + off);
+    v.x = (r.x > 0.f ? v.x : v.x * p.alpha) * p.gain;
+    v.y = (r.y > 0.f ? v.y : v.y * p.alpha) * p.gain;
+    v.z = (r.z > 0.f ? v.z : v.z * p.alpha) * p.gain;
+    v.w = (r.w > 0.f ? v.w : v.w * p.alpha) * p.gain;
+    bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+  }
+}  // already flipped and zero-extended: k[ky][kx] meets in[oy+ky-pad][ox+kx-pad]
 
 __device__ __forceinline__ float4 fma4(const float4& a, float s, const float4& acc) {
   return make_float4(fmaf(a.x, s, acc.x), fmaf(a.y, s, acc.y), fmaf(a.z, s, acc.z), fmaf(a.w, s, acc.w));
@@ -75,9 +98,10 @@ __device__ __forceinline__ float4 mul4(const float4& a, float s) { return make_f
 // L1/LSU traffic per output drops from 4 loads to (XT+3)/XT (the kernel is L1-wavefront bound
 // otherwise: at HBM rate 4 loads + 1 store per element would need ~115 B/clk/SM of the 128 available).
 // general (non-separable) 4x4 taps: every input row is folded into three pending output rows
-template <int ROWS, int XT, bool EPI>
+template <int ROWS, int XT, int EPI>
 __device__ __forceinline__ void blur4_general(float* __restrict__ out, const float* __restrict__ x,
-                                              const float* __restrict__ bias, const UpfirdnParams& p, const Taps4& tp) {
+                                              const float* __restrict__ bias, const UpfirdnParams& p, const Taps4& tp,
+                                              const float* __restrict__ ref, float4& bsum) {
   const bool sep = false;
   float kx[4], kyv[4];
 #pragma unroll
@@ -98,7 +122,8 @@ __device__ __forceinline__ void blur4_general(float* __restrict__ out, const flo
   float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
   const int64_t orow = (int64_t)p.out_w * p.minor;
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI) b4 = *reinterpret_cast<const float4*>(bias + c);
+  if (EPI == 1) b4 = *reinterpret_cast<const float4*>(bias + c);
+  const float* refp = EPI == 2 ? ref + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c : nullptr;
 
   bool colok[XT + 3];
 #pragma unroll
@@ -145,12 +170,7 @@ __device__ __forceinline__ void blur4_general(float* __restrict__ out, const flo
       s1[j] = make_float4(s0[j].x + h[1].x, s0[j].y + h[1].y, s0[j].z + h[1].z, s0[j].w + h[1].w);
       s0[j] = h[0];
       if (oy >= oy0 && ox0 + j < p.out_w) {
-        if (EPI) {
-          done.x = lrelu(done.x + b4.x, p.alpha) * p.gain;
-          done.y = lrelu(done.y + b4.y, p.alpha) * p.gain;
-          done.z = lrelu(done.z + b4.z, p.alpha) * p.gain;
-          done.w = lrelu(done.w + b4.w, p.alpha) * p.gain;
-        }
+        blur_epilogue<EPI>(done, b4, p, refp, (int64_t)oy * orow + (int64_t)j * p.minor, bsum);
         st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, done);
       }
     }
@@ -193,10 +213,11 @@ __device__ __forceinline__ f2x2 ldg_f2x2(const float* p) {
   return f2x2{pack2(v.x, v.y), pack2(v.z, v.w)};
 }
 
-template <int XT, bool EPI, bool INTERIOR>
+template <int XT, int EPI, bool INTERIOR>
 __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const float* __restrict__ xin, const UpfirdnParams& p,
                                                const unsigned long long (&kx)[4], const unsigned long long (&ky)[4],
-                                               int ox0, int ix0, int oy0, int oy1, const float4& b4) {
+                                               int ox0, int ix0, int oy0, int oy1, const float4& b4,
+                                               const float* __restrict__ refp, float4& bsum) {
   const int64_t orow = (int64_t)p.out_w * p.minor;
   const int64_t irow = (int64_t)p.in_w * p.minor;
   bool colok[XT + 3];
@@ -236,12 +257,7 @@ __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const floa
             float4 done;
             unpack2(dl, done.x, done.y);
             unpack2(dh, done.z, done.w);
-            if (EPI) {
-              done.x = lrelu(done.x + b4.x, p.alpha) * p.gain;
-              done.y = lrelu(done.y + b4.y, p.alpha) * p.gain;
-              done.z = lrelu(done.z + b4.z, p.alpha) * p.gain;
-              done.w = lrelu(done.w + b4.w, p.alpha) * p.gain;
-            }
+            blur_epilogue<EPI>(done, b4, p, refp, (op - o) + (int64_t)j * p.minor, bsum);
             st_stream4(op + (int64_t)j * p.minor, done);
           }
         }
@@ -253,10 +269,13 @@ __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const floa
   }
 }
 
-template <int ROWS, int XT, bool EPI>
+template <int ROWS, int XT, int EPI>
 __global__ void __launch_bounds__(128) blur4_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x,
                                                          const float* __restrict__ kernel,
-                                                         const float* __restrict__ bias, UpfirdnParams p) {
+                                                         const float* __restrict__ bias, UpfirdnParams p,
+                                                         const float* __restrict__ ref, float* __restrict__ gbias) {
+  __shared__ float4 red[EPI == 2 ? 128 : 1];
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   // taps: flipped (true convolution) and zero-extended to 4x4; 16 uniform loads per thread
   Taps4 tp;
 #pragma unroll
@@ -270,38 +289,57 @@ __global__ void __launch_bounds__(128) blur4_nhwc_kernel(float* __restrict__ out
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) sep = sep && (tp.k[a][b] * tp.k[0][0] == tp.k[a][0] * tp.k[0][b]);
-  if (!sep) {
-    blur4_general<ROWS, XT, EPI>(out, x, bias, p, tp);
-    return;
-  }
-  unsigned long long kx[4], ky[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float cv = tp.k[i][0] / tp.k[0][0];
-    kx[i] = pack2(tp.k[0][i], tp.k[0][i]);
-    ky[i] = pack2(cv, cv);
-  }
   const int c4n = p.minor >> 2;
   const int groups = (p.out_w + XT - 1) / XT;
   const int lin = blockIdx.x * blockDim.x + threadIdx.x;  // (column group, c4), c4 fastest
-  if (lin >= groups * c4n) return;
-  const int og = lin / c4n;
-  const int c = (lin - og * c4n) << 2;
-  const int ox0 = og * XT;
-  const int m = blockIdx.z;
-  const int oy0 = blockIdx.y * ROWS;
-  const int oy1 = min(oy0 + ROWS, p.out_h);
-  const int ix0 = ox0 - p.pad_x0;
-  const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
-  float* o = out + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI) b4 = *reinterpret_cast<const float4*>(bias + c);
-  const bool interior = ix0 >= 0 && ix0 + XT + 3 <= p.in_w && ox0 + XT <= p.out_w && oy0 - p.pad_y0 >= 0 &&
-                        oy1 - 1 - p.pad_y0 + 3 < p.in_h;
-  if (interior) blur4sep_strip<XT, EPI, true>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4);
-  else blur4sep_strip<XT, EPI, false>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4);
+  const bool active = lin < groups * c4n;
+  if (!sep) {
+    blur4_general<ROWS, XT, EPI>(out, x, bias, p, tp, ref, bsum);
+  } else if (active) {
+    unsigned long long kx[4], ky[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float cv = tp.k[i][0] / tp.k[0][0];
+      kx[i] = pack2(tp.k[0][i], tp.k[0][i]);
+      ky[i] = pack2(cv, cv);
+    }
+    const int og = lin / c4n;
+    const int c = (lin - og * c4n) << 2;
+    const int ox0 = og * XT;
+    const int m = blockIdx.z;
+    const int oy0 = blockIdx.y * ROWS;
+    const int oy1 = min(oy0 + ROWS, p.out_h);
+    const int ix0 = ox0 - p.pad_x0;
+    const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
+    const int64_t obase = (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
+    float* o = out + obase;
+    const float* refp = EPI == 2 ? ref + obase : nullptr;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI == 1) b4 = *reinterpret_cast<const float4*>(bias + c);
+    const bool interior = ix0 >= 0 && ix0 + XT + 3 <= p.in_w && ox0 + XT <= p.out_w && oy0 - p.pad_y0 >= 0 &&
+                          oy1 - 1 - p.pad_y0 + 3 < p.in_h;
+    if (interior) blur4sep_strip<XT, EPI, true>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum);
+    else blur4sep_strip<XT, EPI, false>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum);
+  }
+  if (EPI == 2 && gbias != nullptr) {
+    // bias gradient: fold the replicas of each channel group inside the CTA (blockDim is a multiple of c4n or
+    // c4n a multiple of blockDim: thread t always owns channel group (blockIdx.x*128 + t) % c4n), then one
+    // atomic per channel per CTA
+    red[threadIdx.x] = bsum;
+    __syncthreads();
+    const int first = (int)((int64_t)blockIdx.x * blockDim.x % c4n);
+    const int span = c4n < (int)blockDim.x ? c4n : (int)blockDim.x;   // distinct channel groups in this CTA
+    if ((int)threadIdx.x < span) {
+      float4 sacc = red[threadIdx.x];
+      for (int t = threadIdx.x + c4n; t < (int)blockDim.x; t += c4n) {
+        const float4 q = red[t];
+        sacc.x += q.x; sacc.y += q.y; sacc.z += q.z; sacc.w += q.w;
+      }
+      float* dst = gbias + (((first + threadIdx.x) % c4n) << 2);
+      atomicAdd(dst + 0, sacc.x); atomicAdd(dst + 1, sacc.y); atomicAdd(dst + 2, sacc.z); atomicAdd(dst + 3, sacc.w);
+    }
+  }
 }
-
 
 // ---------------------------------------------------------------------------------------
 // resampling fast paths (separable taps, <= 4x4, NHWC, minor % 4 == 0):
@@ -569,8 +607,8 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
     const int c4n = minor / 4;
     constexpr int ROWS = 32, XT = 4;
     dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
-    if (bias) blur4_nhwc_kernel<ROWS, XT, true><<<grid, 128, 0, st>>>(out, x, kernel, bias, p);
-    else blur4_nhwc_kernel<ROWS, XT, false><<<grid, 128, 0, st>>>(out, x, kernel, bias, p);
+    if (bias) blur4_nhwc_kernel<ROWS, XT, 1><<<grid, 128, 0, st>>>(out, x, kernel, bias, p, nullptr, nullptr);
+    else blur4_nhwc_kernel<ROWS, XT, 0><<<grid, 128, 0, st>>>(out, x, kernel, bias, p, nullptr, nullptr);
     IDEAS_CHECK_LAUNCH("upfirdn2d(fast)");
     return IDEAS_OK;
   }
@@ -595,5 +633,39 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
   upfirdn2d_generic_kernel<<<(int)blocks, 256, 0, st>>>(out, x, kernel, bias, p, total);
   IDEAS_CHECK_LAUNCH("upfirdn2d(generic)");
+  return IDEAS_OK;
+}
+
+// Backward of  y = act(u) -> z = blur(y)  in one pass:  gx = blur^T(gz) * (ref > 0 ? 1 : alpha) * gain, where blur^T is
+// upfirdn2d with the caller-supplied (already flipped) kernel and gradient pads, `ref` = y (same shape as gx) and
+// gbias[c] += sum over everything but the channel of gx (may be NULL).  Replaces UpFirDn2dBackward followed by
+// FusedLeakyReLUFunctionBackward (upfirdn2d.py:19-42 + fused_act.py:20-49): the blurred gradient is never written.
+extern "C" int ideas_blur_act_backward(float* gx, float* gbias, const float* g, const float* ref, const float* kernel,
+                                       int major, int in_h, int in_w, int minor, int kernel_h, int kernel_w,
+                                       int pad_x0, int pad_x1, int pad_y0, int pad_y1, float alpha, float gain,
+                                       void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IDEAS_REQUIRE(major >= 0 && in_h >= 1 && in_w >= 1 && minor >= 1, "blur_act_backward: bad input shape");
+  IDEAS_REQUIRE(kernel_h >= 1 && kernel_w >= 1, "blur_act_backward: empty FIR kernel");
+  UpfirdnParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
+  p.up_x = p.up_y = p.down_x = p.down_y = 1; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
+  p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
+  p.alpha = alpha; p.gain = gain;
+  IDEAS_REQUIRE(p.out_h >= 1 && p.out_w >= 1, "blur_act_backward: padding/cropping leaves no output");
+  if (major == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(gx && g && ref && kernel, "blur_act_backward: null pointer");
+  const int c4n = minor / 4;
+  const bool fast = kernel_h <= 4 && kernel_w <= 4 && minor % 4 == 0 && aligned16(gx) && aligned16(g) && aligned16(ref) &&
+                    major <= 65535 && (c4n <= 128 ? 128 % c4n == 0 : c4n % 128 == 0);
+  if (!fast) {
+    set_error("blur_act_backward: needs a <= 4x4 kernel, channels %% 4 == 0 and a power-of-two channel count (C=%d)", minor);
+    return IDEAS_ERR_UNSUPPORTED;
+  }
+  constexpr int ROWS = 32, XT = 4;
+  dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
+  blur4_nhwc_kernel<ROWS, XT, 2><<<grid, 128, 0, st>>>(gx, g, kernel, nullptr, p, ref, gbias);
+  IDEAS_CHECK_LAUNCH("blur_act_backward");
   return IDEAS_OK;
 }

@@ -102,9 +102,10 @@ class ConvLayer(nn.Sequential):
         super().__init__(*stages)
         self.padding = conv_pad
 
-    def forward(self, input):
+    def forward(self, input, start=0):
+        """``start``: index of the first child to run (ResBlock fuses conv1's tail with conv2's leading Blur)."""
         mods = list(self)
-        i, out = 0, input
+        i, out = start, input
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
@@ -158,7 +159,17 @@ class ResBlock(nn.Module):
                                   bias=False, activate=False)
 
     def forward(self, input):
-        out = self.conv2(self.conv1(input))
+        c1, c2 = list(self.conv1), list(self.conv2)
+        if (input.is_cuda and isinstance(c2[0], Blur) and len(c1) >= 2 and isinstance(c1[-1], FusedLeakyReLU)
+                and isinstance(c1[-2], EqualConv2d) and c1[-2].bias is None):
+            # conv1 -> FusedLeakyReLU -> Blur as one autograd node: its backward fuses the blur's and the
+            # activation's backward passes into one kernel (the blurred gradient is never written)
+            h = input
+            for m in c1[:-2]:                      # ReflectionPad2d of the encoder blocks
+                h = m(h)
+            out = self.conv2(c1[-2].forward_act_blur(h, c1[-1], c2[0]), start=1)
+        else:
+            out = self.conv2(self.conv1(input))
         skip = input if self.skip is None else self.skip(input)
         return add_scale(out, skip, _INV_SQRT2)
 

@@ -102,6 +102,16 @@ class EqualConv2d(nn.Module):
         return _ops.conv2d(input, wp, self.bias, K=self.weight.shape[0], kh=k, kw=k, stride=stride,
                            pad=self.padding)
 
+    def forward_act_blur(self, input, activation: FusedLeakyReLU, blur: "Blur"):
+        """Blur(activation(conv(input))) with the fused backward of ``ConvActBlur``."""
+        if self.bias is not None:
+            raise RuntimeError("EqualConv2d: a fused activation brings its own bias")
+        k = self.weight.shape[2]
+        wp = PackWeight.apply(self.weight, False, self.scale)
+        g = Geom.forward(input.shape, self.weight.shape[0], k, k, self.stride, self.padding)
+        return _ops.ConvActBlur.apply(input, wp, activation.bias, g, activation.negative_slope, activation.scale,
+                                      blur.kernel, tuple(blur.pad))
+
     def __repr__(self):
         return (f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]},"
                 f" {self.weight.shape[2]}, stride={self.stride}, padding={self.padding})")

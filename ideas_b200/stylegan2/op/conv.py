@@ -210,6 +210,54 @@ class ConvWgrad(Function):
         return g_x, g_dy, None
 
 
+def _blur_act_bwd_ok(channels: int) -> bool:
+    c4 = channels // 4
+    return channels % 4 == 0 and ((c4 <= 128 and 128 % c4 == 0) or c4 % 128 == 0)
+
+
+class ConvActBlur(Function):
+    """z = Blur(gain * lrelu(conv(x, w) + b)): conv1 -> FusedLeakyReLU -> Blur of a down-sampling ResBlock
+    (reference models.py:213-227 with :49-134).  Forward is the two kernels it always was; the point is the
+    backward: the blur's backward and the activation's backward run as ONE kernel (ideas_blur_act_backward), so the
+    blurred gradient never makes an HBM round trip.  Under create_graph=True (the R1 penalty, utils.py:112-118)
+    the backward is instead composed of the differentiable pieces, exactly as without the fusion."""
+
+    @staticmethod
+    def forward(ctx, x, wp, bias, g: Geom, alpha, gain, kernel, pad):
+        require_cuda(x, wp, bias, kernel)
+        x = nhwc(x)
+        kernel = kernel.contiguous()
+        _check(x, (g.N, g.C, g.H, g.W), "conv forward input")
+        y = _fwd(x, wp, g, bias=bias, act=_lib.ACT_LRELU, alpha=alpha, gain=gain)
+        pad4 = (pad[0], pad[1], pad[0], pad[1])
+        z = _upfirdn_run(y, kernel, (1, 1), (1, 1), pad4)
+        ctx.save_for_backward(x, wp, y, kernel, torch.flip(kernel, [0, 1]))
+        ctx.cfg = (g, alpha, gain, pad4, (z.shape[2], z.shape[3]))
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, wp, y, kernel, gkernel = ctx.saved_tensors
+        g, alpha, gain, pad4, zhw = ctx.cfg
+        want_bias = ctx.needs_input_grad[2]
+        g_pad = _grad_pad((y.shape[2], y.shape[3]), zhw, kernel.shape, (1, 1), (1, 1), pad4)
+        if torch.is_grad_enabled() or not _blur_act_bwd_ok(g.K):
+            gy = UpFirDn2dBackward.apply(gz, kernel, gkernel, (1, 1), (1, 1), pad4, g_pad, tuple(y.shape), zhw)
+            g1, gb = FusedLeakyReLUFunctionBackward.apply(gy, y, want_bias, alpha, gain)
+            gx = ConvDgrad.apply(g1, wp, g) if ctx.needs_input_grad[0] else None
+            gw = ConvWgrad.apply(x, g1, g) if ctx.needs_input_grad[1] else None
+            return gx, gw, (gb if want_bias else None), None, None, None, None, None
+        gz = nhwc(gz)
+        g1 = torch.empty_like(y)
+        gb = torch.zeros(g.K, device=y.device, dtype=y.dtype) if want_bias else None
+        kh, kw = gkernel.shape
+        _lib.call("ideas_blur_act_backward", ptr(g1), ptr(gb), ptr(gz), ptr(y), ptr(gkernel), g.N, gz.shape[2], gz.shape[3],
+                  g.K, kh, kw, g_pad[0], g_pad[1], g_pad[2], g_pad[3], float(alpha), float(gain), stream_ptr(gz))
+        gx = _dgrad(g1, wp, g) if ctx.needs_input_grad[0] else None
+        gw = _wgrad(x, g1, g) if ctx.needs_input_grad[1] else None
+        return gx, gw, gb, None, None, None, None, None
+
+
 def conv2d(x, wp, bias=None, *, K, kh, kw, stride=1, pad=0, act=False, alpha=0.2, gain=2 ** 0.5):
     """y = [lrelu](conv(x, w) + bias) with packed weights (see PackWeight)."""
     g = Geom.forward(x.shape, K, kh, kw, stride, pad)

@@ -110,6 +110,17 @@ int ideas_upfirdn2d(float* out, const float* x, const float* kernel,
                     int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                     const float* bias, float alpha, float gain, void* stream);
 
+/* Backward of the pair  y = act(u) -> z = Blur(y)  (conv1 -> FusedLeakyReLU -> Blur of a down-sampling
+ * ResBlock, reference models.py:213-227) in one pass:
+ *   gx = upfirdn2d(g, kernel, pads) * (ref > 0 ? 1 : alpha) * gain,   gbias[c] += sum of gx over all but the channel
+ * `g` (major, in_h, in_w, minor) is the gradient w.r.t. z, `kernel` / pads are those of the blur's own backward
+ * (flipped kernel, upfirdn2d.py:31-42), `ref` = y has the shape of gx.  Replaces UpFirDn2dBackward followed by
+ * FusedLeakyReLUFunctionBackward (upfirdn2d.py:19-42, fused_act.py:20-49) without writing the blurred gradient.
+ * gbias may be NULL; IDEAS_ERR_UNSUPPORTED outside the fast-path envelope (caller runs the two ops). */
+int ideas_blur_act_backward(float* gx, float* gbias, const float* g, const float* ref, const float* kernel,
+                            int major, int in_h, int in_w, int minor, int kernel_h, int kernel_w,
+                            int pad_x0, int pad_x1, int pad_y0, int pad_y1, float alpha, float gain, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A1/A5  convolutions (new native unit; the reference calls cuDNN here)
  *

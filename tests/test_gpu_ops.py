@@ -361,3 +361,41 @@ def test_patchify_matches_interpolate_loop(B, C, H, W, n_crop):
     # device-resident boxes give the same result (CUDA-graph path)
     got2 = U.patchify_image(ic, n_crop, crops=U.crops_to_device(crops, "cuda"))
     assert torch.equal(got2, got)
+
+
+@pytest.mark.parametrize("C,K,H", [(32, 64, 20), (64, 128, 33), (32, 384, 12), (64, 1024, 9), (8, 20, 16)])
+def test_conv_act_blur_fused_backward(C, K, H):
+    """ConvActBlur (conv -> FusedLeakyReLU -> Blur as one node, backward = one blur^T * mask kernel) against the
+    same three ops as separate autograd nodes; K = 384 / 20 take the documented fallback inside the node.  Also the
+    create_graph path (what the R1 penalty uses) against the unfused double backward."""
+    from ideas_b200 import _lib as L
+    from ideas_b200.stylegan2.op import conv as CV
+    from ideas_b200.stylegan2.op import fused_leaky_relu, upfirdn2d
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(2, C, H, H, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    wp = torch.randn(9, K, C, device="cuda", generator=g) / (9 * C) ** 0.5
+    b = torch.randn(K, device="cuda", generator=g)
+    k = (O.make_kernel([1, 3, 3, 1])).cuda()
+    gz = torch.randn(2, K, H + 1, H + 1, device="cuda", generator=g)
+    geom = CV.Geom.forward(x.shape, K, 3, 3, 1, 1)
+
+    def fused(xx, ww, bb):
+        return CV.ConvActBlur.apply(xx, ww, bb, geom, 0.2, 2 ** 0.5, k, (2, 2))
+
+    def split(xx, ww, bb):
+        y = CV.ConvFwd.apply(xx, ww, bb, geom, L.ACT_LRELU, 0.2, 2 ** 0.5)
+        return upfirdn2d(y, k, pad=(2, 2))
+
+    outs = []
+    for fn in (fused, split):
+        xx, ww, bb = x.clone().requires_grad_(True), wp.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        z = fn(xx, ww, bb)
+        gx, gw, gb = torch.autograd.grad(z, [xx, ww, bb], gz)
+        # second order: d/dw of |dz/dx . gz|^2, as in an R1 penalty
+        xx2, ww2 = x.clone().requires_grad_(True), wp.clone().requires_grad_(True)
+        z2 = fn(xx2, ww2, b)
+        (g1,) = torch.autograd.grad(z2.sum(), xx2, create_graph=True)
+        (ggw,) = torch.autograd.grad(g1.pow(2).sum(), ww2)
+        outs.append((z, gx, gw, gb, ggw))
+    for a, c, name in zip(outs[0], outs[1], ("z", "gx", "gw", "gb", "ggw")):
+        assert rel(a, c) <= 2e-5, (name, rel(a, c))

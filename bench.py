@@ -300,6 +300,12 @@ def run_ours(args):
         d2h = 0
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # e2e: every step copies its batch from pinned host memory and its loss scalars back to pinned host
+        # memory; the host consumes step k-1's losses while step k runs (the asynchronous logging a training
+        # loop does), and the last step's losses before the clock stops
+        host_losses = [torch.zeros(16).pin_memory() for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        seen = 0.0
         with sampler:
             ev0.record()
             for k in range(args.steps):
@@ -307,10 +313,18 @@ def run_ours(args):
                 if e2e:
                     X = pool[k % 2].to(dev, non_blocking=True)
                     losses = tr.step(X, it)
-                    host = torch.stack([v.detach().reshape(()) for v in losses.values()]).cpu()
-                    d2h = host.numel() * 4
+                    vals = torch.stack([v.detach().reshape(()) for v in losses.values()])
+                    host_losses[k % 2][:vals.numel()].copy_(vals, non_blocking=True)
+                    copied[k % 2].record()
+                    d2h = vals.numel() * 4
+                    if k > 0:
+                        copied[(k - 1) % 2].synchronize()
+                        seen += float(host_losses[(k - 1) % 2][0])
                 else:
                     tr.step(resident[k % 2], it)
+            if e2e:
+                copied[(args.steps - 1) % 2].synchronize()
+                seen += float(host_losses[(args.steps - 1) % 2][0])
             ev1.record()
             barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -351,9 +365,16 @@ def run_ours(args):
                 t, cores, _ = cpu_reference_step_time(S, 1, 0)
                 line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port",
                                         "sample": f"1 train iteration on 1 image {S}x{S} (oracle port of train.py:33-221), {t:.1f} s"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graphs hold NCCL work: tearing the communicator down while they are alive can block at
+        # exit (observed: the JSON line printed, then destroy_process_group never returned).  Everything is
+        # measured and printed; leave together and skip the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

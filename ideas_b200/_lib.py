@@ -47,6 +47,7 @@ _PROTOTYPES = {
     "ideas_scale_channels": [_P, _P, _P, c_int, c_int64, c_int, _P],
     "ideas_channel_dot": [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P],
     "ideas_add_scale": [_P, _P, _P, c_float, c_int64, _P],
+    "ideas_reflect_pad2d": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "ideas_patchify_forward": [_P, _P, _P] + [c_int] * 7 + [_P],
     "ideas_patchify_backward": [_P, _P, _P] + [c_int] * 7 + [_P],
     "ideas_bits_encode": [_P, _P, _P, c_int, c_int, c_int, c_float, _P],

@@ -28,6 +28,8 @@
 
 namespace ideas {
 
+void set_blur_variant(int v);   // upfirdn2d.cu
+
 namespace {
 
 // option "tma_tf32" (default 1): tensor maps declare CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, so the TMA unit
@@ -1075,6 +1077,10 @@ extern "C" int ideas_umma_available(void) { return 1; }
 extern "C" int ideas_set_option(const char* name, int value) {
   if (name && !strcmp(name, "tma_tf32")) {
     ideas::g_tma_tf32.store(value ? 1 : 0);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "blur_variant")) {
+    ideas::set_blur_variant(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "wgrad_reuse")) {

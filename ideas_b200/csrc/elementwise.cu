@@ -295,3 +295,91 @@ extern "C" int ideas_patchify_backward(float* gimg, const float* gout, const int
   IDEAS_CHECK_LAUNCH("patchify_backward");
   return IDEAS_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// reflection padding on NHWC data (nn.ReflectionPad2d of the reference's ResBlocks, models.py:102-108).
+// torch's CUDA kernel returns an NCHW-contiguous tensor for a channels_last input (and an NCHW gradient), which
+// costs a layout-conversion copy on each side of every pad; these two gather kernels stay in NHWC.
+//   forward : out[n, y, x, :] = in[n, r(y - p, H), r(x - p, W), :],  r(i, L) = i < 0 ? -i : (i >= L ? 2(L-1) - i : i)
+//   backward: gin[n, y, x, :] = sum of gout over the (<= 3 x 3) padded positions that read (y, x)
+// ---------------------------------------------------------------------------------------
+namespace ideas {
+
+__device__ __forceinline__ int reflect_index(int i, int L) { return i < 0 ? -i : (i >= L ? 2 * (L - 1) - i : i); }
+
+template <typename V>
+__global__ void __launch_bounds__(256) reflect_pad_kernel(V* __restrict__ out, const V* __restrict__ in, int H, int W, int cv,
+                                                          int p, int64_t total) {
+  const int OH = H + 2 * p, OW = W + 2 * p;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % cv);
+    int64_t t = i / cv;
+    const int x = (int)(t % OW);
+    t /= OW;
+    const int y = (int)(t % OH);
+    const int64_t n = t / OH;
+    out[i] = in[((n * H + reflect_index(y - p, H)) * W + reflect_index(x - p, W)) * cv + c];
+  }
+}
+
+__device__ __forceinline__ void acc_add(float& a, const float& b) { a += b; }
+__device__ __forceinline__ void acc_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void acc_zero(float& a) { a = 0.f; }
+__device__ __forceinline__ void acc_zero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// padded coordinates that read source index i (axis length L, pad p): i + p, and the two mirror images
+__device__ __forceinline__ int reflect_sources(int i, int L, int p, int (&o)[3]) {
+  int n = 0;
+  o[n++] = i + p;
+  if (i >= 1 && i <= p) o[n++] = p - i;
+  if (i >= L - 1 - p && i <= L - 2) o[n++] = p + 2 * (L - 1) - i;
+  return n;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) reflect_pad_bwd_kernel(V* __restrict__ gin, const V* __restrict__ gout, int H, int W,
+                                                              int cv, int p, int64_t total) {
+  const int OH = H + 2 * p, OW = W + 2 * p;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % cv);
+    int64_t t = i / cv;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H);
+    const int64_t n = t / H;
+    int ys[3], xs[3];
+    const int ny = reflect_sources(y, H, p, ys), nx = reflect_sources(x, W, p, xs);
+    V acc;
+    acc_zero(acc);
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b) acc_add(acc, gout[((n * OH + ys[a]) * OW + xs[b]) * cv + c]);
+    gin[i] = acc;
+  }
+}
+
+}  // namespace ideas
+
+extern "C" int ideas_reflect_pad2d(float* out, const float* x, int N, int H, int W, int C, int pad, int backward,
+                                   void* stream) {
+  IDEAS_REQUIRE(N >= 0 && H >= 1 && W >= 1 && C >= 1, "reflect_pad2d: bad shape");
+  IDEAS_REQUIRE(pad >= 0 && pad < H && pad < W, "reflect_pad2d: padding %d must be smaller than the input (%dx%d)", pad, H, W);
+  if (N == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(out && x, "reflect_pad2d: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = C % 4 == 0 && ideas::aligned16(out) && ideas::aligned16(x);
+  const int cv = vec ? C / 4 : C;
+  // `out` is the padded tensor in the forward and the un-padded gradient in the backward
+  const int64_t total = backward ? (int64_t)N * H * W * cv : (int64_t)N * (H + 2 * pad) * (W + 2 * pad) * cv;
+  const int blocks = blocks_for(total, 256, 8);
+  if (vec) {
+    if (backward) ideas::reflect_pad_bwd_kernel<float4><<<blocks, 256, 0, st>>>((float4*)out, (const float4*)x, H, W, cv, pad, total);
+    else ideas::reflect_pad_kernel<float4><<<blocks, 256, 0, st>>>((float4*)out, (const float4*)x, H, W, cv, pad, total);
+  } else {
+    if (backward) ideas::reflect_pad_bwd_kernel<float><<<blocks, 256, 0, st>>>(out, x, H, W, cv, pad, total);
+    else ideas::reflect_pad_kernel<float><<<blocks, 256, 0, st>>>(out, x, H, W, cv, pad, total);
+  }
+  IDEAS_CHECK_LAUNCH("reflect_pad2d");
+  return IDEAS_OK;
+}

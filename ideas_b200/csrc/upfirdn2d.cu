@@ -16,7 +16,14 @@
 // Upsample/Downsample/ADA -- goes through a direct-form kernel with the same semantics.
 #include "common.cuh"
 
+#include <atomic>
+#include <type_traits>
+
 namespace ideas {
+
+static std::atomic<int> g_blur_variant{0};
+int blur_variant() { return g_blur_variant.load(); }
+void set_blur_variant(int v) { g_blur_variant.store(v); }
 
 struct UpfirdnParams {
   int major, in_h, in_w, minor, kh, kw;
@@ -605,7 +612,21 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
                     minor % 4 == 0 && aligned16(out) && aligned16(x) && (!bias || aligned16(bias)) && major <= 65535;
   if (fast) {
     const int c4n = minor / 4;
-    constexpr int ROWS = 32, XT = 4;
+    const int variant = ideas::blur_variant();
+    if (!bias && variant != 0) {                    // tuning variants (option "blur_variant"), plain blur only
+      auto launch = [&](auto rows, auto xt) {
+        constexpr int R = decltype(rows)::value, X = decltype(xt)::value;
+        dim3 grid(ceil_div(ceil_div(p.out_w, X) * c4n, 128), ceil_div(p.out_h, R), major);
+        blur4_nhwc_kernel<R, X, 0><<<grid, 128, 0, st>>>(out, x, kernel, bias, p, nullptr, nullptr);
+      };
+      if (variant == 1) launch(std::integral_constant<int, 32>{}, std::integral_constant<int, 4>{});
+      else if (variant == 2) launch(std::integral_constant<int, 64>{}, std::integral_constant<int, 4>{});
+      else launch(std::integral_constant<int, 64>{}, std::integral_constant<int, 2>{});
+      IDEAS_CHECK_LAUNCH("upfirdn2d(fast)");
+      return IDEAS_OK;
+    }
+    // 32 rows x 2 columns per thread: scripts/blur_variants.py (x4 columns: 1-17 % slower, 127 registers)
+    constexpr int ROWS = 32, XT = 2;
     dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
     if (bias) blur4_nhwc_kernel<ROWS, XT, 1><<<grid, 128, 0, st>>>(out, x, kernel, bias, p, nullptr, nullptr);
     else blur4_nhwc_kernel<ROWS, XT, 0><<<grid, 128, 0, st>>>(out, x, kernel, bias, p, nullptr, nullptr);
@@ -663,7 +684,7 @@ extern "C" int ideas_blur_act_backward(float* gx, float* gbias, const float* g, 
     set_error("blur_act_backward: needs a <= 4x4 kernel, channels %% 4 == 0 and a power-of-two channel count (C=%d)", minor);
     return IDEAS_ERR_UNSUPPORTED;
   }
-  constexpr int ROWS = 32, XT = 4;
+  constexpr int ROWS = 32, XT = 2;
   dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
   blur4_nhwc_kernel<ROWS, XT, 2><<<grid, 128, 0, st>>>(gx, g, kernel, nullptr, p, ref, gbias);
   IDEAS_CHECK_LAUNCH("blur_act_backward");

@@ -23,7 +23,7 @@ from .stylegan2.model import (Blur, EqualConv2d, EqualLinear, ScaledLeakyReLU,
 from .stylegan2.op import FusedLeakyReLU, upfirdn2d
 from .stylegan2.op import conv as _ops
 from .stylegan2.op.conv import PackWeight
-from .stylegan2.op.elementwise import add_scale
+from .stylegan2.op.elementwise import add_scale, reflect_pad
 
 _INV_SQRT2 = 1.0 / math.sqrt(2.0)
 
@@ -64,6 +64,20 @@ def _blur_pads(blur_kernel, kernel_size, up):
     return ((p + 1) // 2, p // 2)
 
 
+class ReflectionPad2d(nn.Module):
+    """nn.ReflectionPad2d on the NHWC kernel (parameter-free: no state_dict entry either way)."""
+
+    def __init__(self, padding):
+        super().__init__()
+        self.padding = int(padding)
+
+    def forward(self, input):
+        return reflect_pad(input, self.padding)
+
+    def extra_repr(self):
+        return str(self.padding)
+
+
 class ConvLayer(nn.Sequential):
     """[Blur] conv | convT Blur | [ReflectionPad] conv, then FusedLeakyReLU / ScaledLeakyReLU / Tanh.
     Child order and indices follow models.py:49-134 exactly (they are the state_dict keys)."""
@@ -87,7 +101,7 @@ class ConvLayer(nn.Sequential):
                     conv_pad = half
                 elif padding == "reflect":
                     if half > 0:
-                        stages.append(nn.ReflectionPad2d(half))
+                        stages.append(ReflectionPad2d(half))
                 elif padding != "valid":
                     raise ValueError('Padding should be "zero", "reflect", or "valid"')
             stages.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=conv_pad,

@@ -183,6 +183,12 @@ int ideas_channel_dot(float* dot, float* out, const float* a, const float* b, co
 /* out = (a + b) * gain   (the residual merge (out+skip)/sqrt(2), models.py:178,227) */
 int ideas_add_scale(float* out, const float* a, const float* b, float gain, int64_t n, void* stream);
 
+/* nn.ReflectionPad2d(pad) on NHWC data (reference models.py:102-108: reflect-padded 3x3 convs of the encoder,
+ * structure-generator and extractor ResBlocks).  backward = 0: out (N, H+2p, W+2p, C) from x (N, H, W, C);
+ * backward = 1: out (N, H, W, C) = gradient w.r.t. the un-padded tensor from x = gradient (N, H+2p, W+2p, C).
+ * H and W are always the UN-padded sizes. */
+int ideas_reflect_pad2d(float* out, const float* x, int N, int H, int W, int C, int pad, int backward, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A10 / SURVEY §8(f)-1  patchify: n_crop boxes (device int32 (n_crop,4) = y,x,h,w, shared by the batch)
  * cut from every NHWC image and resized to (th,tw) with F.interpolate(bilinear, align_corners=False)

@@ -399,3 +399,28 @@ def test_conv_act_blur_fused_backward(C, K, H):
         outs.append((z, gx, gw, gb, ggw))
     for a, c, name in zip(outs[0], outs[1], ("z", "gx", "gw", "gb", "ggw")):
         assert rel(a, c) <= 2e-5, (name, rel(a, c))
+
+
+@pytest.mark.parametrize("C,H,W,pad", [(32, 16, 16, 1), (64, 9, 31, 1), (8, 5, 4, 2), (3, 7, 6, 1), (4, 2, 3, 1), (128, 64, 64, 1)])
+def test_reflect_pad_nhwc_fwd_bwd_double_bwd(C, H, W, pad):
+    """NHWC reflection padding against torch's F.pad(mode="reflect") on the CPU (nn.ReflectionPad2d of the
+    reference, models.py:102-108): forward, gradient (adjoint gather) and double backward; bit-exact (pure copies
+    and <= 9-term sums in a fixed order can differ only by summation order)."""
+    from ideas_b200.stylegan2.op.elementwise import reflect_pad
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, C, H, W, generator=g)
+
+    def run(fn, dev):
+        xx = x.to(dev).requires_grad_(True)
+        out = fn(xx)
+        gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(42)).to(dev).requires_grad_(True)
+        (gx,) = torch.autograd.grad(out, xx, gy, create_graph=True)
+        (ggy,) = torch.autograd.grad(gx.pow(2).sum(), gy)
+        return out, gx, ggy
+
+    got = run(lambda t: reflect_pad(t, pad), "cuda")
+    want = run(lambda t: torch.nn.functional.pad(t, (pad,) * 4, mode="reflect"), "cpu")
+    assert torch.equal(got[0].cpu(), want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert a.shape == b.shape and rel(a, b) <= 1e-6
+    assert got[0].is_contiguous(memory_format=torch.channels_last) or C == 1

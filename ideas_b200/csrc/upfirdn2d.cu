@@ -79,15 +79,14 @@ struct Taps4 { float k[4][4]; };
 //   EPI 2: v * (ref > 0 ? 1 : alpha) * gain, per-thread channel sums    (backward of act -> Blur: the blurred
 //          gradient meets the mask of the activation that fed the blur; the sums are the bias gradient)
 template <int EPI>
-__device__ __forceinline__ void blur_epilogue(float4& v, const float4& b4, const UpfirdnParams& p, const float* ref,
-                                              int64_t off, float4& bsum) {
+__device__ __forceinline__ void blur_epilogue(float4& v, const float4& b4, const UpfirdnParams& p, const float4& r,
+                                              float4& bsum) {
   if (EPI == 1) {
     v.x = lrelu(v.x + b4.x, p.alpha) * p.gain;
     v.y = lrelu(v.y + b4.y, p.alpha) * p.gain;
     v.z = lrelu(v.z + b4.z, p.alpha) * p.gain;
     v.w = lrelu(v.w + b4.w, p.alpha) * p.gain;
   } else if (EPI == 2) {
-    const float4 r = ld_stream4(ref + off);
     v.x = (r.x > 0.f ? v.x : v.x * p.alpha) * p.gain;
     v.y = (r.y > 0.f ? v.y : v.y * p.alpha) * p.gain;
     v.z = (r.z > 0.f ? v.z : v.z * p.alpha) * p.gain;
@@ -177,7 +176,9 @@ __device__ __forceinline__ void blur4_general(float* __restrict__ out, const flo
       s1[j] = make_float4(s0[j].x + h[1].x, s0[j].y + h[1].y, s0[j].z + h[1].z, s0[j].w + h[1].w);
       s0[j] = h[0];
       if (oy >= oy0 && ox0 + j < p.out_w) {
-        blur_epilogue<EPI>(done, b4, p, refp, (int64_t)oy * orow + (int64_t)j * p.minor, bsum);
+        float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == 2) rv = ld_stream4(refp + (int64_t)oy * orow + (int64_t)j * p.minor);
+        blur_epilogue<EPI>(done, b4, p, rv, bsum);
         st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, done);
       }
     }
@@ -249,6 +250,14 @@ __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const floa
 #pragma unroll
         for (int i = 0; i < XT + 3; ++i)
           r[i] = (rowok && colok[i]) ? ldg_f2x2(rp + (int64_t)i * p.minor) : f2x2{0ull, 0ull};
+        // EPI 2: the mask operand of the row this iteration completes is fetched together with the input row, so it
+        // is in flight during the arithmetic instead of being a dependent load in the epilogue
+        float4 refv[XT];
+#pragma unroll
+        for (int j = 0; j < XT; ++j) {
+          refv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI == 2 && oy >= oy0 && (INTERIOR || ox0 + j < p.out_w)) refv[j] = ld_stream4(refp + (op - o) + (int64_t)j * p.minor);
+        }
 #pragma unroll
         for (int j = 0; j < XT; ++j) {
           f2x2 a;
@@ -264,7 +273,7 @@ __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const floa
             float4 done;
             unpack2(dl, done.x, done.y);
             unpack2(dh, done.z, done.w);
-            blur_epilogue<EPI>(done, b4, p, refp, (op - o) + (int64_t)j * p.minor, bsum);
+            blur_epilogue<EPI>(done, b4, p, refv[j], bsum);
             st_stream4(op + (int64_t)j * p.minor, done);
           }
         }

@@ -42,6 +42,18 @@ for (B, C, H, pd) in ((32, 128, 256, 2), (32, 64, 256, 1), (32, 256, 128, 2), (9
     print(f"blur {B}x{C}x{H}^2 pad{pd}: " + "  ".join(f"v{v} {r:6.0f} GB/s" for v, r in enumerate(res)), flush=True)
     del x, y
 
+# fused blur^T * activation-mask backward (ideas_blur_act_backward): bytes = gz read + y read + gx write
+for (B, C, H) in ((32, 128, 256), (32, 256, 128), (32, 64, 256), (96, 512, 64)):
+    gz = torch.randn(B, H + 1, H + 1, C, device=dev)
+    yv = torch.randn(B, H, H, C, device=dev)
+    gx = torch.empty_like(yv)
+    gb = torch.zeros(C, device=dev)
+    for name, gbp in (("no bias grad", None), ("bias grad", gb)):
+        t = timeit(lambda: _lib.call("ideas_blur_act_backward", ptr(gx), ptr(gbp), ptr(gz), ptr(yv), ptr(kk), B, H + 1, H + 1, C, 4, 4,
+                                     1, 1, 1, 1, 0.2, 2 ** 0.5, stream_ptr(gz)))
+        print(f"blur_act_backward {B}x{C}x{H}^2 ({name}): {t * 1e3:.3f} ms  {4.0 * (gz.numel() + 2 * yv.numel()) / t / 1e9:6.0f} GB/s", flush=True)
+    del gz, yv, gx
+
 x = torch.randn(4, 32, 64, 64, device=dev).contiguous(memory_format=torch.channels_last)
 p = torch.nn.functional.pad(x, (1, 1, 1, 1), mode="reflect")
 print("reflection_pad2d(channels_last input): output channels_last-contiguous =", p.is_contiguous(memory_format=torch.channels_last),

@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--prune-dead-backward", action="store_true",
+                    help="NOT the default measurement: restrict the loop's second backward (train.py:214-216) to Ex's parameters")
     return ap.parse_args()
 
 
@@ -275,7 +277,8 @@ def run_ours(args):
     _lib.lib()
     B, S = args.batch, args.image_size
     targs = default_args(batch_size=B, image_size=S)
-    tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs)   # same seed on every rank => identical replicas
+    tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
+                 prune_dead_backward=args.prune_dead_backward)
     tr.broadcast_parameters(0)
     import random
     torch.manual_seed(1000 + rank)                   # per-rank data / Z / T2 / crops
@@ -341,6 +344,7 @@ def run_ours(args):
         "dtype": "tf32" if _lib.umma_enabled() else "f32", "data": "synthetic",
         "config": {"workload": workload_name(B, S), "global_batch": B * world, "parallelism": f"dp{world}",
                    "r1_iterations_in_window": r1_in_window, "cuda_graphs": not args.no_graphs,
+                   "second_backward": "Ex parameters only (pruned)" if args.prune_dead_backward else "full graph, as train.py:214-216",
                    "l2": "activations of one step are tens of GB, far larger than the 126 MB L2; no explicit flush",
                    "est_tflops": FLOP_PER_IMAGE_STEP * value / 1e12 if S == 256 else None},
         "clocks": clocks, "gpu_launches": launches,

@@ -77,7 +77,8 @@ class Trainer:
     """The ``trainer`` dict of train.py:390-432 as an object (``trainer[key]`` still works)."""
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
-                 states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None):
+                 states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
+                 prune_dead_backward: bool = False):
         self.args = args
         self.device = torch.device(device)
         self.cuda_graphs = bool(cuda_graphs and self.device.type == "cuda")
@@ -86,6 +87,12 @@ class Trainer:
         # the main branch, and autograd replays the same streams in backward.  Same arithmetic, same results.
         self.multi_stream = bool((self.cuda_graphs if multi_stream is None else multi_stream) and self.device.type == "cuda")
         self._side_streams: List[torch.cuda.Stream] = []
+        # train.py:214-216 runs Ex_loss.backward() over the whole retained graph, although only ex_optim.step()
+        # follows: the gradients it adds to E / G / Gstru are discarded by the next g_optim.zero_grad().  With this
+        # flag the second backward is restricted to Ex's parameters -- same parameter trajectory, ~10 % fewer FLOPs
+        # (SURVEY.md App. B).  Off by default: the .grad fields of E / G / Gstru then differ from the reference's
+        # between iterations, and bench.py measures the reference's loop as written.
+        self.prune_dead_backward = bool(prune_dead_backward)
         self._graphs: Dict[tuple, tuple] = {}
         self.replayed_launches = 0        # library kernels launched through graph replays (see bench.py gpu_launches)
         self._pool = None
@@ -341,7 +348,10 @@ class Trainer:
         Loss_total.backward(retain_graph=True)
         self.g_optim.step()
         self.ex_optim.zero_grad()
-        Ex_loss.backward()
+        if self.prune_dead_backward:
+            Ex_loss.backward(inputs=[p for p in t["Ex"].parameters()])
+        else:
+            Ex_loss.backward()
         self.ex_optim.step()
         for k in EMA_KEYS:
             accumulate(t[k + "_ema"], t[k], self.accum)

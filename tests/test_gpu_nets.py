@@ -239,3 +239,23 @@ def test_graph_replay_multi_stream_matches_single_stream():
         for k in a:
             assert math.isfinite(a[k]) and math.isfinite(b[k])
             assert abs(a[k] - b[k]) <= tol * max(1.0, abs(a[k])), (it, k, a[k], b[k])
+
+
+def test_pruned_second_backward_same_parameters():
+    """Trainer(prune_dead_backward=True) restricts train.py:214-216's second backward to Ex's parameters.  Starting
+    from the same weights and draws, one eager iteration must leave every network with the same parameters as the
+    full second backward (only the discarded .grad fields of E / G / Gstru differ)."""
+    from ideas_b200.train_step import Trainer, default_args
+    cfg = dict(channel=4, texture_channel=64, N=1, image_size=256, batch_size=2, d_reg_every=16)
+    X = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(3)) * 2 - 1).cuda()
+    draws = _draws(2, 1, 16, 64, 256, 256, 8, 4)
+    runs = []
+    for prune in (False, True):
+        tr = Trainer(default_args(**cfg), device="cuda", seed=13, fused_adam=False, prune_dead_backward=prune)
+        tr.step(X, 1, draws)
+        torch.cuda.synchronize()
+        runs.append({k: torch.cat([p.detach().reshape(-1) for p in tr.nets[k].parameters()]) for k in ("E", "G", "Gstru", "Ex")})
+    for k in runs[0]:
+        d = (runs[0][k] - runs[1][k]).abs()
+        # the weight-gradient merge uses fp32 atomics: allow the +-lr flips of ~0 gradients (see the graph test above)
+        assert float((d > 1e-5).float().mean()) < 0.02, (k, float(d.max()))

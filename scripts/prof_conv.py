@@ -10,6 +10,9 @@ import torch
 from ideas_b200 import _lib
 from ideas_b200._tensor import ptr, stream_ptr
 
+for kv in filter(None, os.environ.get("IDEAS_OPTS", "").split(",")):      # e.g. IDEAS_OPTS=halo_resident=0
+    name, val = kv.split("=")
+    _lib.call("ideas_set_option", name.encode(), int(val))
 kind = sys.argv[1]
 N, C, K, H, k, s, pad = (int(v) for v in sys.argv[2:9])
 iters = int(sys.argv[9]) if len(sys.argv) > 9 else 5

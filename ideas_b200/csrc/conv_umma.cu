@@ -347,6 +347,15 @@ struct alignas(64) HaloParams {
   TapH taps[kMaxTaps];
 };
 
+__device__ __forceinline__ void st_global_pred(float* p, float v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q st.global.f32 [%0], %1;\n\t}"
+      ::"l"(p), "f"(v), "r"((int)pred)
+      : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -510,7 +519,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
           float r = fmaf(v[i], os, bs);
           r = (lrelu_on && r < 0.f) ? r * alpha : r;
           r *= gain;
-          if (ok) r0[wrap * row_step + xi * pix_step] = r;
+          // predicated store, no branch: with two epilogue warps per scheduler a branch per element showed up as
+          // branch-resolving stalls on every store (ncu source view), and the epilogue warps were busy 70 % of the
+          // kernel at 128 input channels -- the bottleneck below that
+          st_global_pred(r0 + (wrap * row_step + xi * pix_step), r, ok);
         }
       }
       // every tcgen05.ld of this warp has completed (wait::ld): hand the accumulator back

@@ -24,6 +24,7 @@ from torch.nn import functional as F
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 from .op import conv as _ops
 from .op.conv import Geom, ModConv, ModConvUp, PackWeight
+from .._tensor import nhwc
 
 
 class PixelNorm(nn.Module):
@@ -178,7 +179,11 @@ class ModulatedConv2d(nn.Module):
         """Returns the modulated convolution; with ``activation`` the FusedLeakyReLU (bias,
         slope, gain) is applied inside the same kernels (StyledConv passes its own)."""
         k = self.kernel_size
-        s = self.modulation(style)                                   # (B, Cin)
+        if input.is_cuda:
+            # layout conversion OUTSIDE the autograd nodes below: they save their inputs for the double backward
+            # (path-length regularisation), which must stay connected to the caller's graph
+            input = nhwc(input)
+        s = self.modulation(style).contiguous()                      # (B, Cin)
         ws = self.weight[0] * self.scale                             # temp, never the leaf (see op/conv.py)
         d = None
         if self.demodulate:

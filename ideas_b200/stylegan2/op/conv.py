@@ -276,6 +276,49 @@ def _umma_shape_ok(g: Geom) -> bool:
     return _lib.umma_enabled() and g.C % 32 == 0 and g.K % 32 == 0
 
 
+def _act_or_bias(z, bias, act, alpha, gain):
+    from .fused_act import fused_leaky_relu
+    if act:
+        return fused_leaky_relu(z, bias, alpha, gain)
+    return z if bias is None else z + bias.view(1, -1, 1, 1)
+
+
+def _modconv_composite(x, s, d, wp, bias, g: Geom, act, alpha, gain):
+    """ModConv written with the differentiable building blocks (each has a double backward): used to differentiate
+    the backward itself (create_graph=True: path-length regularisation, stylegan2/train.py:85-98)."""
+    xm = x * s.view(g.N, g.C, 1, 1)
+    u = ConvFwd.apply(xm, wp, None, g, _lib.ACT_NONE, 0.2, 1.0)
+    if d is not None:
+        u = u * d.view(g.N, g.K, 1, 1)
+    return _act_or_bias(u, bias, act, alpha, gain)
+
+
+def _modconv_up_composite(x, s, d, wp, kernel, blur_pad, bias, g: Geom, act, alpha, gain):
+    from .upfirdn2d import UpFirDn2d
+    xm = x * s.view(g.N, g.K, 1, 1)
+    u = ConvDgrad.apply(xm, wp, g)
+    if d is not None:
+        u = u * d.view(g.N, g.C, 1, 1)
+    z = UpFirDn2d.apply(u, kernel, (1, 1), (1, 1), blur_pad)
+    return _act_or_bias(z, bias, act, alpha, gain)
+
+
+def _grad_of_composite(fn, tensors, needs, gy):
+    """Gradients of ``fn(*tensors)`` w.r.t. the tensors flagged in ``needs``, themselves differentiable: the
+    forward is recomputed from the (graph-connected) saved inputs under enable_grad."""
+    with torch.enable_grad():
+        # Aliases make the inputs independent variables of the composite: the saved tensors are interior nodes of
+        # the caller's graph (the demodulation d is itself a function of the style s), and differentiating w.r.t.
+        # them directly would fold the d -> s path into ds as well as returning dd (counted twice by the caller's
+        # graph).  The views keep the results connected to the originals for the second differentiation.
+        alias = [t.view_as(t) if (t is not None and t.requires_grad) else t for t in tensors]
+        out = fn(*alias)
+        wanted = [a for a, n in zip(alias, needs) if n and a is not None and a.requires_grad]
+        grads = torch.autograd.grad(out, wanted, gy, create_graph=True, allow_unused=True) if wanted else ()
+    it = iter(grads)
+    return [next(it) if (n and t is not None and t.requires_grad) else None for t, n in zip(tensors, needs)]
+
+
 class ModConv(Function):
     """out = gain * lrelu(d[n,k] * conv(s[n,c] * x, w)[n,k] + bias[k])   (same resolution).
 
@@ -306,10 +349,22 @@ class ModConv(Function):
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, gy):
         x, s, d, wp, bias, out, xm = ctx.saved_tensors
         g = ctx.g
+        if torch.is_grad_enabled():
+            # create_graph=True: differentiate a recomputed composite instead of the fused kernels.  The bias leaf
+            # was saved as a detached copy (train.py:209-216), so second-order terms do not reach it; none exist
+            # (the output is piecewise linear in the bias).
+            act, alpha, gain = ctx.act, ctx.alpha, ctx.gain
+            gx, gs, gd, gw, _ = _grad_of_composite(
+                lambda x_, s_, d_, w_, b_: _modconv_composite(x_, s_, d_, w_, b_, g, act, alpha, gain),
+                [x, s, d, wp, bias], list(ctx.needs_input_grad[:4]) + [False], gy)
+            gb = None
+            if bias is not None and ctx.needs_input_grad[4]:
+                mask = torch.where(out > 0, 1.0, alpha) * gain if act else 1.0
+                gb = (gy * mask).sum(dim=(0, 2, 3))
+            return gx, gs, gd, gw, gb, None, None, None, None
         gy = nhwc(gy)
         st = stream_ptr(gy)
         P = g.OH * g.OW
@@ -374,14 +429,23 @@ class ModConvUp(Function):
         kernel = blur_kernel.contiguous()
         out = _upfirdn_run(u, kernel, (1, 1), (1, 1), blur_pad, bias=bias if act else None, alpha=alpha, gain=gain)
         ctx.g, ctx.act, ctx.alpha, ctx.gain, ctx.blur_pad = g, act, alpha, gain, blur_pad
-        ctx.save_for_backward(x, s, d, wp, kernel, u, out if act else None, xm)
+        ctx.save_for_backward(x, s, d, wp, kernel, u, out if act else None, xm,
+                              bias.clone() if (act and bias is not None) else None)
         return out
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, gy):
-        x, s, d, wp, kernel, u, out, xm = ctx.saved_tensors
+        x, s, d, wp, kernel, u, out, xm, bias_copy = ctx.saved_tensors
         g = ctx.g
+        if torch.is_grad_enabled():
+            act, alpha, gain, blur_pad = ctx.act, ctx.alpha, ctx.gain, ctx.blur_pad
+            gx, gs, gd, gw, _ = _grad_of_composite(
+                lambda x_, s_, d_, w_, b_: _modconv_up_composite(x_, s_, d_, w_, kernel, blur_pad, b_, g, act, alpha, gain),
+                [x, s, d, wp, bias_copy], list(ctx.needs_input_grad[:4]) + [False], gy)
+            gb = None
+            if act and ctx.needs_input_grad[6]:
+                gb = (gy * torch.where(out > 0, 1.0, alpha) * gain).sum(dim=(0, 2, 3))
+            return gx, gs, gd, gw, None, None, gb, None, None, None, None
         gy = nhwc(gy)
         st = stream_ptr(gy)
         gb = None

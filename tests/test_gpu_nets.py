@@ -259,3 +259,39 @@ def test_pruned_second_backward_same_parameters():
         d = (runs[0][k] - runs[1][k]).abs()
         # the weight-gradient merge uses fp32 atomics: allow the +-lr flips of ~0 gradients (see the graph test above)
         assert float((d > 1e-5).float().mean()) < 0.02, (k, float(d.max()))
+
+
+def test_sender_receiver_pipeline_matches_oracle():
+    """ideas_b200.pipeline: message -> Gstru -> G -> image -> E -> Ex -> message on untrained 64x64 networks, against
+    the oracle networks on the CPU run on the same secret tensor (train.py:254-286).  Untrained nets do not recover
+    the message; the contract is that both implementations decode the SAME bits wherever the extractor's output is
+    not within 1e-3 of a decision threshold, and that the BER is computed consistently."""
+    from ideas_b200 import pipeline as P
+    from ideas_b200 import utils as U
+    from ideas_b200.models import init_model
+    from ideas_b200.train_step import default_args
+    torch.manual_seed(31)
+    a = default_args(image_size=64)
+    nets = {k: init_model(c, a) for k, c in (("E", "DisentanglementEncoder"), ("G", "Generator"),
+                                              ("Gstru", "StructureGenerator"), ("Ex", "TensorExtractor"))}
+    sds = {k: {n: t.detach().clone() for n, t in m.state_dict().items()} for k, m in nets.items()}
+    for m in nets.values():
+        m.cuda().eval()
+    B, hw = 4, 4
+    M = torch.randint(0, 2, (B, hw * hw), generator=torch.Generator().manual_seed(32)).float()
+    T = torch.rand(B, a.texture_channel, generator=torch.Generator().manual_seed(33)) * 2 - 1
+    torch.manual_seed(34)                                   # the jitter draw of message_to_tensor
+    img = P.hide(nets, M, T.cuda(), sigma=1, delta=0.5, N=1, image_size=64)
+    assert tuple(img.shape) == (B, 3, 64, 64)
+    got = P.extract(nets, img, sigma=1)
+    torch.manual_seed(34)
+    Z = U.message_to_tensor(M, 1, 0.5).reshape(B, 1, hw, hw).cpu()
+    with torch.no_grad():
+        img_ref = ON.generator(sds["G"], ON.structure_generator(sds["Gstru"], Z), T)
+        zhat_ref = ON.extractor(sds["Ex"], ON.encoder(sds["E"], img_ref)[0]).reshape(B, -1)
+    assert float((img.cpu() - img_ref).abs().max() / img_ref.abs().max()) <= 1e-2
+    want = torch.from_numpy(OB.tensor_to_message(zhat_ref.numpy(), 1))
+    safe = (zhat_ref.abs() > 1e-3)                          # sigma = 1: the threshold is z = 0 (up to fp32 rounding)
+    assert torch.equal(got.cpu()[safe], want[safe])
+    ber = P.round_trip_ber(nets, M, T.cuda(), sigma=1, delta=0.5, N=1, image_size=64)
+    assert 0.0 <= ber <= 1.0

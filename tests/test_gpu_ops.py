@@ -424,3 +424,44 @@ def test_reflect_pad_nhwc_fwd_bwd_double_bwd(C, H, W, pad):
     for a, b in zip(got[1:], want[1:]):
         assert a.shape == b.shape and rel(a, b) <= 1e-6
     assert got[0].is_contiguous(memory_format=torch.channels_last) or C == 1
+
+
+@pytest.mark.parametrize("cin,cout,res,up", [(32, 64, 8, False), (64, 32, 8, True)])
+def test_styled_conv_path_length_second_order(cin, cout, res, up):
+    """Path-length regularisation (stylegan2/train.py:85-98): the gradient of <y, noise> w.r.t.
+    the style, taken with create_graph=True, squared and back-propagated into the layer's parameters and input --
+    i.e. the double backward of the modulated convolution -- against the oracle on the CPU.  Runs on the exact-fp32
+    FFMA kernels so the comparison is tight."""
+    from ideas_b200 import _lib as L
+    from ideas_b200.stylegan2 import model as M
+    from ideas_b200.stylegan2.op import conv as CV
+    old = CV.set_default_impl(L.IMPL_SIMT)
+    try:
+        torch.manual_seed(21)
+        m = M.StyledConv_without_noise(cin, cout, 3, 24, upsample=up)
+        m.activate.bias.data.normal_()
+        x = torch.randn(2, cin, res, res)
+        st = torch.rand(2, 24) * 2 - 1
+        sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "kernel" not in k)
+              for k, v in m.state_dict().items()}
+        names = ["conv.weight", "conv.modulation.weight", "conv.modulation.bias"]
+
+        def pl(fn_out, style, leaves):
+            noise = torch.randn(fn_out.shape, generator=torch.Generator().manual_seed(22)).to(fn_out.device)
+            (g,) = torch.autograd.grad((fn_out * noise).sum(), style, create_graph=True)
+            penalty = g.pow(2).sum(1).mean()
+            return penalty, torch.autograd.grad(penalty, leaves)
+
+        xr, sr = x.clone().requires_grad_(True), st.clone().requires_grad_(True)
+        want = O.styled_conv(xr, sr, sd["conv.weight"], sd["conv.modulation.weight"], sd["conv.modulation.bias"],
+                             sd["activate.bias"], upsample=up, blur_kernel=sd.get("conv.blur.kernel"))
+        p_want, g_want = pl(want, sr, [xr] + [sd[n] for n in names])
+        m = m.cuda()
+        xc, sc = x.cuda().requires_grad_(True), st.cuda().requires_grad_(True)
+        params = dict(m.named_parameters())
+        p_got, g_got = pl(m(xc, sc), sc, [xc] + [params[n] for n in names])
+        assert abs(float(p_got) - float(p_want)) <= 1e-4 * abs(float(p_want))
+        for name, a, b in zip(["dx"] + names, g_got, g_want):
+            assert rel(a, b) <= 2e-3, (name, rel(a, b))      # gradients through the leaky-ReLU mask: a few flips
+    finally:
+        CV.set_default_impl(old)

@@ -55,6 +55,16 @@ def test_argument_validation_without_a_gpu():
     assert L.ideas_fused_bias_act(p0, p0, p0, p0, 3, 0, 0.2, 1.0, 0, 1, 1, p0) == 0
     assert L.ideas_conv2d_forward(p0, p0, p0, p0, p0, p0, 0, 8, 8, 4, 4, 3, 3, 1, 1, 0, 0.2, 1.0, 0, p0) == 0
     assert L.ideas_bits_decode(p0, p0, 0, 16, 1, p0) == 0
+    # the two entry points added for the fused backward / NHWC reflection pad
+    assert L.ideas_blur_act_backward(p0, p0, p0, p0, p0, 1, 0, 4, 4, 4, 4, 1, 1, 1, 1, 0.2, 1.0, p0) == -1      # in_h = 0
+    assert L.ideas_blur_act_backward(p0, p0, p0, p0, p0, 0, 4, 4, 4, 4, 4, 1, 1, 1, 1, 0.2, 1.0, p0) == 0       # empty batch
+    assert L.ideas_reflect_pad2d(p0, p0, 1, 4, 4, 4, 4, 0, p0) == -1                                            # pad >= size
+    assert b"padding" in L.ideas_last_error()
+    assert L.ideas_reflect_pad2d(p0, p0, 0, 4, 4, 4, 1, 0, p0) == 0
+    # tuning knobs: known names accepted, unknown rejected with a message
+    assert L.ideas_set_option(b"halo", 1) == 0 and L.ideas_set_option(b"wgrad_reuse", 1) == 0
+    assert L.ideas_set_option(b"no_such_option", 1) == -1
+    assert b"unknown option" in L.ideas_last_error()
 
 
 def test_product_never_imports_the_oracle():
@@ -78,3 +88,11 @@ def test_ops_fail_loudly_without_cuda():
         fused_leaky_relu(torch.randn(1, 4, 2, 2), torch.zeros(4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         upfirdn2d(torch.randn(1, 4, 8, 8), make_kernel([1, 3, 3, 1]), pad=(2, 1))
+
+
+def test_pipeline_validates_message_length():
+    """ideas_b200.pipeline.hide checks the message geometry before touching the device (train.py:254-257)."""
+    import torch
+    from ideas_b200 import pipeline
+    with pytest.raises(ValueError, match="sigma\\*N\\*h\\*w"):
+        pipeline.hide({}, torch.zeros(2, 100), torch.zeros(2, 2048), sigma=1, N=1, image_size=256)

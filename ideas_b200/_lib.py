@@ -62,15 +62,33 @@ def launch_count() -> int:
     return int(lib().ideas_launch_count())
 
 
+def _source_digest() -> str:
+    """sha256 over every CUDA source, header and the compile flags: the library is stale exactly when this changes
+    (modification times do not survive the snapshot that carries the tree to a GPU box)."""
+    import hashlib
+    deps = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))])
+    deps.append(os.path.join(_HERE, "..", "include", "ideas_b200.h"))
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    for d in deps:
+        with open(d, "rb") as f:
+            h.update(os.path.basename(d).encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
+def _is_current(digest: str) -> bool:
+    try:
+        with open(LIB_PATH + ".srchash") as f:
+            return os.path.exists(LIB_PATH) and f.read().strip() == digest
+    except OSError:
+        return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into ideas_b200/lib/libideas_b200.so."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(_HERE, "..", "include", "ideas_b200.h"))
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(d) for d in deps)
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+    digest = _source_digest()
+    if not force and _is_current(digest):
+        return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -95,6 +113,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed: %s\n%s" % (" ".join(cmd), r.stdout))
     os.replace(tmp, LIB_PATH)
+    with open(LIB_PATH + ".srchash", "w") as f:
+        f.write(digest)
     return LIB_PATH
 
 
@@ -106,8 +126,7 @@ def lib() -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            build()
+        build()                              # no-op when the library matches the sources (content digest)
         L = ctypes.CDLL(LIB_PATH)
         for name, argtypes in _PROTOTYPES.items():
             fn = getattr(L, name)           # AttributeError if the symbol is not exported

@@ -1,7 +1,10 @@
 """Launcher: run the reference's train.py UNMODIFIED on the B200 implementation.
 
     python -m ideas_b200.compat.run_train /path/to/IDEAS/train.py --exp_name demo \
-        --dataset_type synthetic --dataset_path none --batch_size 32 ...
+        --dataset_type normal --dataset_path /data/ffhq --num_iters 80000 --batch_size 32 ...
+
+``--dataset_path synthetic[:length]`` (with either dataset type) selects LSUN-shaped random tensors instead of
+files (ideas_b200/compat/dataset.py); ``lmdb`` needs the `lmdb` package.
 
 Shims applied outside the reference tree (SURVEY.md App. D -- the reference no longer runs as written
 on torch >= 2.6 / torchvision >= 0.13):

@@ -207,6 +207,19 @@ __device__ __forceinline__ BilinearTap bilinear_tap(int dst, int in_size, int ou
   return t;
 }
 
+// Boxes are data written by the host (or a device RNG): clamp them into the image so that a malformed row can
+// never turn into an out-of-bounds access (a well-formed box is returned unchanged).
+struct CropBox { int y, x, h, w; };
+
+__device__ __forceinline__ CropBox load_box(const int* b, int H, int W) {
+  CropBox c;
+  c.h = min(max(__ldg(b + 2), 1), H);
+  c.w = min(max(__ldg(b + 3), 1), W);
+  c.y = min(max(__ldg(b), 0), H - c.h);
+  c.x = min(max(__ldg(b + 1), 0), W - c.w);
+  return c;
+}
+
 __global__ void __launch_bounds__(256) patchify_fwd_kernel(float* __restrict__ out, const float* __restrict__ img,
                                                            const int* __restrict__ boxes, int B, int H, int W, int C,
                                                            int n_crop, int th, int tw) {
@@ -218,7 +231,8 @@ __global__ void __launch_bounds__(256) patchify_fwd_kernel(float* __restrict__ o
     t /= th;
     const int j = (int)(t % n_crop);
     const int b = (int)(t / n_crop);
-    const int y0 = __ldg(boxes + j * 4), x0 = __ldg(boxes + j * 4 + 1), h = __ldg(boxes + j * 4 + 2), w = __ldg(boxes + j * 4 + 3);
+    const CropBox bx = load_box(boxes + j * 4, H, W);
+    const int y0 = bx.y, x0 = bx.x, h = bx.h, w = bx.w;
     const BilinearTap ty_ = bilinear_tap(ty, h, th), tx_ = bilinear_tap(tx, w, tw);
     const float* base = img + (int64_t)b * H * W * C;
     const float* p00 = base + ((int64_t)(y0 + ty_.i0) * W + (x0 + tx_.i0)) * C;
@@ -243,7 +257,8 @@ __global__ void __launch_bounds__(256) patchify_bwd_kernel(float* __restrict__ g
     t /= th;
     const int j = (int)(t % n_crop);
     const int b = (int)(t / n_crop);
-    const int y0 = __ldg(boxes + j * 4), x0 = __ldg(boxes + j * 4 + 1), h = __ldg(boxes + j * 4 + 2), w = __ldg(boxes + j * 4 + 3);
+    const CropBox bx = load_box(boxes + j * 4, H, W);
+    const int y0 = bx.y, x0 = bx.x, h = bx.h, w = bx.w;
     const BilinearTap ty_ = bilinear_tap(ty, h, th), tx_ = bilinear_tap(tx, w, tw);
     float* base = gimg + (int64_t)b * H * W * C;
     float* p00 = base + ((int64_t)(y0 + ty_.i0) * W + (x0 + tx_.i0)) * C;

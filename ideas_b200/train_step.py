@@ -98,7 +98,7 @@ class Trainer:
         self._pool = None
         self._static_X: Optional[torch.Tensor] = None
         self._static_boxes: Optional[Dict[str, torch.Tensor]] = None
-        self._host_boxes: Optional[Dict[str, torch.Tensor]] = None
+        self._host_boxes: Optional[List[Dict[str, torch.Tensor]]] = None
         if seed is not None:
             torch.manual_seed(seed)
         self.nets: Dict[str, torch.nn.Module] = {}
@@ -211,9 +211,42 @@ class Trainer:
     def _refresh_boxes(self, H, W):
         """Draw this iteration's crop boxes like the reference (CPU RNG) and stage them into the static
         device tensors the captured patchify kernels read."""
+        # two pinned staging sets used alternately: set i is rewritten only after the H2D copies issued from it two
+        # steps ago have completed (event), so a queued copy can never observe the next iteration's boxes
+        slot = self._box_slot
+        self._box_slot ^= 1
+        if self._box_events[slot] is not None:
+            self._box_events[slot].synchronize()
         for key, n in self._box_specs().items():
-            self._host_boxes[key].copy_(torch.tensor(draw_crops(n, H, W), dtype=torch.int32))
-            self._static_boxes[key].copy_(self._host_boxes[key], non_blocking=True)
+            host = self._host_boxes[slot][key]
+            host.copy_(torch.tensor(draw_crops(n, H, W), dtype=torch.int32))
+            self._static_boxes[key].copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._box_events[slot] = ev
+
+    def _snapshot_state(self):
+        nets = {k: [t.detach().clone() for t in list(n.parameters()) + list(n.buffers())] for k, n in self.nets.items()}
+        opts = []
+        for opt in (self.g_optim, self.ex_optim, self.d_optim):
+            opts.append({p: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                         for p, st in opt.state.items()})
+        return nets, opts
+
+    @torch.no_grad()
+    def _restore_state(self, snap):
+        nets, opts = snap
+        for k, n in self.nets.items():
+            torch._foreach_copy_(list(n.parameters()) + list(n.buffers()), nets[k])
+        for opt, saved in zip((self.g_optim, self.ex_optim, self.d_optim), opts):
+            for p, st in opt.state.items():
+                for name, v in st.items():
+                    if not torch.is_tensor(v):
+                        continue
+                    if p in saved and name in saved[p]:
+                        v.copy_(saved[p][name])
+                    else:
+                        v.zero_()          # state created by the warm-up: back to Adam's lazily-initialised zeros
 
     def _step_graphed(self, X, r1, late):
         H, W = X.shape[2], X.shape[3]
@@ -221,11 +254,16 @@ class Trainer:
             self._static_X = torch.empty_like(X)
             self._static_boxes = {k: torch.zeros((n, 4), dtype=torch.int32, device=self.device)
                                   for k, n in self._box_specs().items()}
-            self._host_boxes = {k: torch.zeros((n, 4), dtype=torch.int32).pin_memory() for k, n in self._box_specs().items()}
+            self._host_boxes = [{k: torch.zeros((n, 4), dtype=torch.int32).pin_memory()
+                                 for k, n in self._box_specs().items()} for _ in range(2)]
+            self._box_slot, self._box_events = 0, [None, None]
             self._static_X.copy_(X)
             self._refresh_boxes(H, W)
             # warm-up outside capture (lazy initialisation: Adam state, cuBLAS workspaces, kernel attributes,
             # the flat all-reduce buckets): two eager iterations of the R1 variant, which covers every code path
+            # The warm-up iterations are throw-away: parameters, buffers, EMA copies and Adam state are put back
+            # afterwards, so the first replayed graph is iteration 1 of the trajectory, exactly as in the eager loop.
+            snap = self._snapshot_state()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
@@ -233,6 +271,8 @@ class Trainer:
                     self._step_eager(self._static_X, True, late, None, boxes=self._static_boxes, device_rng=True)
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
+            self._restore_state(snap)
+            del snap
             for opt in (self.g_optim, self.ex_optim, self.d_optim):
                 opt.zero_grad(set_to_none=True)
             torch.cuda.empty_cache()

@@ -26,8 +26,11 @@ def test_reference_train_imports_our_modules():
         assert train.__file__.startswith(REF)
         assert train.init_model is M.init_model
         assert train.patchify_image is U.patchify_image and train.d_r1_loss is U.d_r1_loss
-        assert train.tensor_to_message is U.tensor_to_message and train.accumulate is U.accumulate
-        ds = train.set_dataset(type="synthetic", path=None, transform=None, resolution=32)
+        CU = sys.modules["utils"]                  # the compat alias module (returns the message on the CPU)
+        assert CU.__file__.endswith(os.path.join("compat", "utils.py"))
+        assert train.tensor_to_message is CU.tensor_to_message and train.accumulate is U.accumulate
+        ds = train.set_dataset(type="normal", path="synthetic:8", transform=None, resolution=32)
+        assert len(ds) == 8
         assert tuple(ds[0].shape) == (3, 32, 32) and float(ds[0].min()) >= -1.0
         import torch
         opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1e-3, betas=(0, 0.99))   # train.py:417-426

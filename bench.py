@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--case", default=None, help="run ONE roofline kernel alone (for ncu); see CASES in bench.py")
+    ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--prune-dead-backward", action="store_true",
                     help="NOT the default measurement: restrict the loop's second backward (train.py:214-216) to Ex's parameters")
@@ -113,18 +116,42 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_step_time(image_size, steps, warmup, budget_s=200.0):
-    """The reference algorithm for the path (oracle port of train.py:33-221) on the host cores.
-    One step = one training iteration on ONE synthetic image (bounded sample of the batch-32 workload)."""
+CPU_BATCH = 4          # images per CPU step: a bounded sample of the batch-32 workload
+
+
+def find_reference_tree():
+    """The unmodified reference, when a copy is reachable: /root/reference (build container) or a tree staged for
+    one GPU run under baseline/_ref/IDEAS (scripts/stage_reference.sh; git-ignored, never committed)."""
+    for cand in (os.environ.get("IDEAS_REFERENCE", ""), "/root/reference", os.path.join(ROOT, "baseline", "_ref", "IDEAS")):
+        if cand and os.path.exists(os.path.join(cand, "train.py")) and os.path.exists(os.path.join(cand, "models.py")):
+            return cand
+    return None
+
+
+def cpu_reference_step_time(image_size, steps, warmup, budget_s=150.0, batch=CPU_BATCH):
+    """The reference algorithm for the path on the host cores, one training iteration (train.py:33-221) on ``batch``
+    synthetic images per step.  With a reference tree reachable the UNMODIFIED reference runs (kind "reference",
+    scripts/reference_step.py drives its train() on the CPU through the App. D shims); otherwise the oracle port
+    (kind "port").  Returns (seconds per step, threads, timed steps, kind)."""
     import torch
-    from oracle.train_step import OracleTrainer
     torch.set_num_threads(os.cpu_count() or 1)
+    ref = find_reference_tree()
+    if ref is not None:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import reference_step
+            t, n = reference_step.time_reference(ref, device="cpu", batch=batch, image_size=image_size, steps=steps,
+                                                 warmup=warmup, budget_s=budget_s)
+            return t, torch.get_num_threads(), n, "reference"
+        except Exception as e:       # a broken staged tree must not take the arm down: fall back to the port
+            print(f"[bench] reference tree at {ref} unusable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    from oracle.train_step import OracleTrainer
     tr = OracleTrainer(seed=0, image_size=image_size)
     torch.manual_seed(1)
     times = []
     t_start = time.perf_counter()
     for i in range(warmup + steps):
-        X = torch.rand(1, 3, image_size, image_size) * 2 - 1
+        X = torch.rand(batch, 3, image_size, image_size) * 2 - 1
         t0 = time.perf_counter()
         tr.step(X, i + 1)          # iterations 1.. : lazy R1 falls in only when i+1 is a multiple of 16
         dt = time.perf_counter() - t0
@@ -133,22 +160,24 @@ def cpu_reference_step_time(image_size, steps, warmup, budget_s=200.0):
         # keep the whole arm within a few minutes: stop early (after >= 1 timed step) once the budget is spent
         if times and time.perf_counter() - t_start + dt > budget_s:
             break
-    return sum(times) / len(times), torch.get_num_threads(), len(times)
+    return sum(times) / len(times), torch.get_num_threads(), len(times), "port"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t, cores, timed = cpu_reference_step_time(args.image_size, args.steps, args.warmup)
-    v = 1.0 / t
-    sample = f"1 image per step ({args.image_size}x{args.image_size}), full train iteration on CPU, oracle port of train.py:33-221"
+    t, cores, timed, kind = cpu_reference_step_time(args.image_size, args.steps, min(args.warmup, 1))
+    v = CPU_BATCH / t
+    what = "the unmodified reference (train.py loop)" if kind == "reference" else "oracle port of train.py:33-221"
+    sample = (f"{CPU_BATCH} images per step ({args.image_size}x{args.image_size}), full train iteration on the host cores, "
+              f"{what}; {timed} timed steps within the time budget")
     print(json.dumps({
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": timed, "steps_requested": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": workload_name(args.batch, args.image_size), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -169,94 +198,197 @@ def time_kernel(fn, iters=20, warm=3):
     return a.elapsed_time(b) / iters * 1e-3
 
 
-def roofline_sections(peaks, peak_kind):
-    """Dominant kernels timed alone, live, with CUDA events on the launching (current) stream."""
+def measure_tf32_gemm_peak(seconds=1.5):
+    """cuBLAS TF32 GEMM (fp32 operands, allow_tf32) 8192^3 on this GPU, now: burst = best single launch of 10,
+    sustained = back-to-back launches for ``seconds``.  This is the tensor roofline SURVEY.md §8(d) cfg 3 asks for;
+    MEASURED_PEAKS.json only carries the bf16 figure (kind::tf32 issues at half that rate)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        c = torch.empty(n, n, device="cuda")
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        flops = 2.0 * n ** 3
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        reps = max(8, int(seconds / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        sustained = e0.elapsed_time(e1) * 1e-3 / reps
+        return {"burst": flops / best / 1e12, "sustained": flops / sustained / 1e12,
+                "how": f"torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS), best of 10 / {reps} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def load_traffic():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, one `ncu --set full` capture per
+    kernel) of the bench kernels, committed under profiles/ by scripts/ncu_cases.sh + scripts/ncu_summary.py."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+# ---- the kernels bench.py reports a roofline for; `python bench.py --case NAME` runs one of them alone (the
+# command ncu captures, scripts/ncu_cases.sh) ---------------------------------------------------------------
+def make_case(name):
+    """Returns (fn, work, unit_kind, description): fn launches the kernel once through the C ABI on the current
+    stream; work = algorithmic FLOPs (tensor bound) or bytes (hbm bound) of one launch."""
     import torch
     from ideas_b200 import _lib
     from ideas_b200._tensor import ptr, stream_ptr
     dev = torch.device("cuda")
-    out = {}
-    # --- cfg 3: ModulatedConv2d 512->512 3x3 @64x64, batch 16: the implicit-GEMM forward launch.
-    N, C, K, H = 16, 512, 512, 64
-    x = torch.randn(N, H, H, C, device=dev)                       # NHWC, 134 MB (> 126 MB L2)
-    wp = torch.randn(9, K, C, device=dev) / (C * 9) ** 0.5
-    d = torch.rand(N, K, device=dev) + 0.5
-    bias = torch.randn(K, device=dev)
-    y = torch.empty(N, H, H, K, device=dev)
     impl = _lib.IMPL_AUTO
+    if name in ("conv_fwd_cfg3", "conv_dgrad_cfg3", "conv_wgrad_cfg3"):
+        # cfg 3: ModulatedConv2d 512->512 3x3 @64x64, batch 16 (x is 134 MB > 126 MB L2)
+        N, C, K, H = 16, 512, 512, 64
+        x = torch.randn(N, H, H, C, device=dev)
+        wp = torch.randn(9, K, C, device=dev) / (C * 9) ** 0.5
+        d = torch.rand(N, K, device=dev) + 0.5
+        bias = torch.randn(K, device=dev)
+        y = torch.randn(N, H, H, K, device=dev)
+        flops = 2.0 * N * H * H * K * C * 9
+        if name == "conv_fwd_cfg3":
+            def fn():
+                _lib.call("ideas_conv2d_forward", ptr(y), ptr(x), ptr(wp), ptr(None), ptr(d), ptr(bias), N, H, H, C, K, 3, 3,
+                          1, 1, _lib.ACT_LRELU, 0.2, 2 ** 0.5, impl, stream_ptr(x))
+            return fn, flops, "tensor", "modulated 3x3 conv fwd, 16x512x64x64 -> 512, demod+bias+lrelu fused"
+        if name == "conv_dgrad_cfg3":
+            def fn():
+                _lib.call("ideas_conv2d_dgrad", ptr(x), ptr(y), ptr(wp), ptr(None), ptr(None), ptr(None), N, H, H, C, K, 3, 3,
+                          1, 1, H, H, _lib.ACT_NONE, 0.2, 1.0, impl, stream_ptr(x))
+            return fn, flops, "tensor", "3x3 conv data gradient, cfg-3 shape"
+        dwp = torch.zeros(9, K, C, device=dev)
 
-    def conv():
-        _lib.call("ideas_conv2d_forward", ptr(y), ptr(x), ptr(wp), ptr(None), ptr(d), ptr(bias), N, H, H, C, K, 3, 3, 1, 1,
-                  _lib.ACT_LRELU, 0.2, 2 ** 0.5, impl, stream_ptr(x))
+        def fn():
+            _lib.call("ideas_conv2d_wgrad", ptr(dwp), ptr(x), ptr(y), ptr(None), ptr(None), N, H, H, C, K, 3, 3, 1, 1, H, H,
+                      impl, stream_ptr(x))
+        return fn, flops, "tensor", "3x3 conv weight gradient, cfg-3 shape (16x512x64x64, 512->512)"
+    if name in ("conv_halo_g256", "conv_lowch_e256"):
+        # the widest low-channel layers: 128->128 @256^2 x32 (G / Dreal) and 32->64 @258^2 valid (E, reflection padded)
+        N2, C2, K2, H2, pad = (32, 128, 128, 256, 1) if name == "conv_halo_g256" else (32, 32, 64, 258, 0)
+        OH = H2 + 2 * pad - 2
+        x2 = torch.randn(N2, H2, H2, C2, device=dev)
+        w2 = torch.randn(9, K2, C2, device=dev) / (C2 * 9) ** 0.5
+        y2 = torch.empty(N2, OH, OH, K2, device=dev)
+        b2 = torch.randn(K2, device=dev)
 
-    t = time_kernel(conv, iters=10, warm=2)
-    flops = 2.0 * N * H * H * K * C * 9
-    tf32_peak = peaks["bf16_tflops"] * 0.5
-    umma = _lib.umma_enabled()
-    out["roofline"] = {
-        "kernel": "conv_igemm (modulated 3x3 conv fwd, 16x512x64x64 -> 512, demod+bias+lrelu fused)",
-        "bound": "tensor", "achieved": flops / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-        "frac": flops / t / 1e12 / tf32_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1b_conv_fwd_cfg3.raw.csv);
-        # algorithmic bytes are 277 MB (x 134 + y 134 + packed weights 9.4): weights and part of x are L2 hits
-        "traffic": 163231488 + 83914752,
-        "peak_source": f"{peak_kind} MEASURED_PEAKS.json bf16_tflops {peaks['bf16_tflops']} x 0.5 (kind::tf32 issues at half the bf16 rate)",
-        "frac_of_bf16_peak": flops / t / 1e12 / peaks["bf16_tflops"],
-        "path": "tcgen05 kind::tf32" if umma else "fp32 FFMA (SIMT)", "algorithmic_flops_per_launch": flops,
-        "ms_per_launch": t * 1e3,
-    }
-    # --- cfg-3 weight gradient (same shape)
-    dy = torch.randn(N, H, H, K, device=dev)
-    dwp = torch.zeros(9, K, C, device=dev)
-
-    def wgrad():
-        _lib.call("ideas_conv2d_wgrad", ptr(dwp), ptr(x), ptr(dy), ptr(None), ptr(None), N, H, H, C, K, 3, 3, 1, 1, H, H, impl,
-                  stream_ptr(x))
-
-    t = time_kernel(wgrad, iters=10, warm=2)
-    out["roofline_wgrad"] = {"kernel": "conv_umma_wgrad (cfg-3 shape, 16x512x64x64, 512->512)", "bound": "tensor",
-                             "achieved": flops / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                             "frac": flops / t / 1e12 / tf32_peak, "traffic": None, "ms_per_launch": t * 1e3}
-    del x, y, dy
-    # --- halo-reuse kernel on the widest low-channel layer of G / Dreal: 128 -> 128 at 256x256, batch 32
-    N2, C2, H2 = 32, 128, 256
-    x2 = torch.randn(N2, H2, H2, C2, device=dev)
-    w2 = torch.randn(9, C2, C2, device=dev) / (C2 * 9) ** 0.5
-    y2 = torch.empty(N2, H2, H2, C2, device=dev)
-
-    def conv2():
-        _lib.call("ideas_conv2d_forward", ptr(y2), ptr(x2), ptr(w2), ptr(None), ptr(None), ptr(bias[:C2]), N2, H2, H2, C2, C2, 3, 3,
-                  1, 1, _lib.ACT_LRELU, 0.2, 2 ** 0.5, impl, stream_ptr(x2))
-
-    t = time_kernel(conv2, iters=10, warm=2)
-    f2 = 2.0 * N2 * H2 * H2 * C2 * C2 * 9
-    out["roofline_halo"] = {"kernel": "conv_umma_halo (3x3 conv fwd, 32x128x256x256 -> 128, bias+lrelu fused)", "bound": "tensor",
-                            "achieved": f2 / t / 1e12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": f2 / t / 1e12 / tf32_peak,
-                            # ncu --set full, profiles/r1b_conv_halo_g256.raw.csv; algorithmic 2.148 GB
-                            "traffic": 1076674000 + 1030189000, "ms_per_launch": t * 1e3}
-    del x2, y2
-    # --- cfg 2: Blur pad (2,2), (32,128,256,256) -> (32,128,257,257)
+        def fn():
+            _lib.call("ideas_conv2d_forward", ptr(y2), ptr(x2), ptr(w2), ptr(None), ptr(None), ptr(b2), N2, H2, H2, C2, K2, 3, 3,
+                      1, pad, _lib.ACT_LRELU, 0.2, 2 ** 0.5, impl, stream_ptr(x2))
+        return fn, 2.0 * N2 * OH * OH * C2 * K2 * 9, "tensor", f"3x3 conv fwd, {N2}x{C2}x{H2}x{H2} -> {K2}, bias+lrelu fused"
     B, Cb, Hb = 32, 128, 256
-    xb = torch.randn(B, Hb, Hb, Cb, device=dev)
-    yb = torch.empty(B, Hb + 1, Hb + 1, Cb, device=dev)
     k = torch.tensor([1., 3., 3., 1.], device=dev)
     k = torch.outer(k, k)
     k = (k / k.sum()).contiguous()
+    if name == "blur_cfg2":
+        # cfg 2 (i): Blur pad (2,2), (32,128,256,256) -> (32,128,257,257)
+        xb = torch.randn(B, Hb, Hb, Cb, device=dev)
+        yb = torch.empty(B, Hb + 1, Hb + 1, Cb, device=dev)
 
-    def blur():
-        _lib.call("ideas_upfirdn2d", ptr(yb), ptr(xb), ptr(k), B, Hb, Hb, Cb, 4, 4, 1, 1, 1, 1, 2, 2, 2, 2, ptr(None), 0.2,
-                  1.0, stream_ptr(xb))
+        def fn():
+            _lib.call("ideas_upfirdn2d", ptr(yb), ptr(xb), ptr(k), B, Hb, Hb, Cb, 4, 4, 1, 1, 1, 1, 2, 2, 2, 2, ptr(None), 0.2,
+                      1.0, stream_ptr(xb))
+        return fn, 4.0 * (xb.numel() + yb.numel()), "hbm", "upfirdn2d up=down=1, 4x4, pad (2,2), 32x128x256x256"
+    if name == "blur_act_bwd_cfg2":
+        # backward of conv -> FusedLeakyReLU -> Blur(pad 2,2): blur^T of the gradient, activation mask, bias-grad sums
+        gz = torch.randn(B, Hb + 1, Hb + 1, Cb, device=dev)
+        yact = torch.randn(B, Hb, Hb, Cb, device=dev)
+        g1 = torch.empty_like(yact)
+        gb = torch.zeros(Cb, device=dev)
 
-    t = time_kernel(blur, iters=20, warm=3)
-    nbytes = 4.0 * (xb.numel() + yb.numel())
-    out["roofline_hbm"] = {
-        "kernel": "blur4_nhwc (upfirdn2d up=down=1, 4x4, pad (2,2), 32x128x256x256)", "bound": "hbm",
-        "achieved": nbytes / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / t / 1e9 / peaks["hbm_gbs"],
-        "traffic": 1173469000 + 1033594000,    # ncu --set full, profiles/r1b_blur.raw.csv
-        "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs", "algorithmic_bytes_per_launch": nbytes,
-        "ms_per_launch": t * 1e3,
-    }
+        def fn():
+            _lib.call("ideas_blur_act_backward", ptr(g1), ptr(gb), ptr(gz), ptr(yact), ptr(k), B, Hb + 1, Hb + 1, Cb, 4, 4,
+                      1, 1, 1, 1, 0.2, 2 ** 0.5, stream_ptr(gz))
+        return fn, 4.0 * (gz.numel() + 2 * yact.numel()), "hbm", "fused blur^T x lrelu mask + bias-grad, 32x128x257x257 -> 256x256"
+    if name in ("lrelu_fwd_cfg2", "lrelu_bwd_cfg2"):
+        # cfg 2 (iii): FusedLeakyReLU(128) on (32,128,256,256)
+        xa = torch.randn(B, Hb, Hb, Cb, device=dev)
+        ba = torch.randn(Cb, device=dev)
+        ya = torch.empty_like(xa)
+        n = xa.numel()
+        if name == "lrelu_fwd_cfg2":
+            def fn():
+                _lib.call("ideas_fused_bias_act", ptr(ya), ptr(xa), ptr(ba), ptr(None), 3, 0, 0.2, 2 ** 0.5, n, 1, Cb, stream_ptr(xa))
+            return fn, 8.0 * n + 4 * Cb, "hbm", "FusedLeakyReLU fwd, 32x128x256x256 (NHWC)"
+        gba = torch.zeros(Cb, device=dev)
+
+        def fn():
+            _lib.call("ideas_bias_act_backward", ptr(ya), ptr(gba), ptr(xa), ptr(xa), 0.2, 2 ** 0.5, n, 1, Cb, stream_ptr(xa))
+        return fn, 12.0 * n + 4 * Cb, "hbm", "FusedLeakyReLU bwd (input grad + bias grad in one pass), 32x128x256x256"
+    raise KeyError(name)
+
+
+CASES = {"roofline": "conv_fwd_cfg3", "roofline_dgrad": "conv_dgrad_cfg3", "roofline_wgrad": "conv_wgrad_cfg3",
+         "roofline_halo": "conv_halo_g256", "roofline_lowch": "conv_lowch_e256", "roofline_hbm": "blur_cfg2",
+         "roofline_blur_act_bwd": "blur_act_bwd_cfg2", "roofline_lrelu_fwd": "lrelu_fwd_cfg2",
+         "roofline_lrelu_bwd": "lrelu_bwd_cfg2"}
+
+
+def roofline_sections(peaks, peak_kind):
+    """Dominant kernels timed alone, live, with CUDA events on the launching (current) stream."""
+    import torch
+    from ideas_b200 import _lib
+    out = {}
+    tf32 = measure_tf32_gemm_peak()
+    out["tf32_gemm_peak"] = tf32
+    traffic = load_traffic()
+    umma = _lib.umma_enabled()
+    half_bf16 = peaks["bf16_tflops"] * 0.5
+    for key, case in CASES.items():
+        fn, work, bound, desc = make_case(case)
+        t = time_kernel(fn, iters=10, warm=3)
+        tr = traffic.get(case, {})
+        if bound == "tensor":
+            ach = work / t / 1e12
+            # peak = the larger of the two tf32 anchors, so the fraction is never flattered: cuBLAS TF32 GEMM measured
+            # here a moment ago (burst), and half of the driver-measured bf16 burst (kind::tf32 issues at half rate)
+            peak = max(tf32["burst"], half_bf16)
+            sec = {"kernel": f"{case}: {desc}", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                   "frac": ach / peak, "traffic": tr.get("dram_bytes"), "traffic_source": tr.get("source"),
+                   "peak_source": f"max(cuBLAS TF32 GEMM burst measured in this run {tf32['burst']:.1f}, {peak_kind} "
+                                  f"MEASURED_PEAKS.json bf16_tflops {peaks['bf16_tflops']} x 0.5 = {half_bf16:.1f})",
+                   "frac_of_cublas_tf32_burst": ach / tf32["burst"], "frac_of_cublas_tf32_sustained": ach / tf32["sustained"],
+                   "frac_of_bf16_peak": ach / peaks["bf16_tflops"],
+                   "path": "tcgen05 kind::tf32" if umma else "fp32 FFMA (SIMT)", "algorithmic_flops_per_launch": work,
+                   "ms_per_launch": t * 1e3}
+        else:
+            ach = work / t / 1e9
+            sec = {"kernel": f"{case}: {desc}", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": ach / peaks["hbm_gbs"], "traffic": tr.get("dram_bytes"), "traffic_source": tr.get("source"),
+                   "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs", "algorithmic_bytes_per_launch": work,
+                   "ms_per_launch": t * 1e3}
+        out[key] = sec
+        del fn
+        torch.cuda.empty_cache()
     return out
+
+
+def run_case(args):
+    """`bench.py --case NAME [--iters N]`: launch one bench kernel alone (what scripts/ncu_cases.sh profiles)."""
+    import torch
+    torch.cuda.set_device(0)
+    fn, work, bound, desc = make_case(args.case)
+    t = time_kernel(fn, iters=args.iters, warm=2)
+    rate = work / t / (1e12 if bound == "tensor" else 1e9)
+    print(json.dumps({"case": args.case, "desc": desc, "ms_per_launch": t * 1e3, "rate": rate,
+                      "unit": "TFLOP/s" if bound == "tensor" else "GB/s"}))
 
 
 def run_ours(args):
@@ -309,10 +441,12 @@ def run_ours(args):
         host_losses = [torch.zeros(16).pin_memory() for _ in range(2)]
         copied = [torch.cuda.Event() for _ in range(2)]
         seen = 0.0
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         with sampler:
             ev0.record()
             for k in range(args.steps):
                 it = args.warmup + 1 + k                 # R1 falls in whenever it % 16 == 0
+                marks[k].record()
                 if e2e:
                     X = pool[k % 2].to(dev, non_blocking=True)
                     losses = tr.step(X, it)
@@ -328,29 +462,38 @@ def run_ours(args):
             if e2e:
                 copied[(args.steps - 1) % 2].synchronize()
                 seen += float(host_losses[(args.steps - 1) % 2][0])
+            marks[args.steps].record()
             ev1.record()
             barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), _lib.launch_count() + tr.replayed_launches - l0, sampler.summary(), d2h
+        per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps)]
+        return float(ms.item()), _lib.launch_count() + tr.replayed_launches - l0, sampler.summary(), d2h, per_step
 
-    ms, launches, clocks, _ = timed(False)
+    ms, launches, clocks, _, per_step = timed(False)
     value = B * world * args.steps / (ms * 1e-3)
-    r1_in_window = sum(1 for k in range(args.steps) if (args.warmup + 1 + k) % targs.d_reg_every == 0)
+    r1_steps = [k for k in range(args.steps) if (args.warmup + 1 + k) % targs.d_reg_every == 0]
+    r1_in_window = len(r1_steps)
+    ms_r1 = [per_step[k] for k in r1_steps]
+    ms_plain = [per_step[k] for k in range(args.steps) if k not in r1_steps]
+    mean = lambda v: (sum(v) / len(v)) if v else None  # noqa: E731
+    # amortised over the loop's 16-iteration lazy-R1 period (train.py:105): 15 plain + 1 R1 iteration
+    amort = (15 * mean(ms_plain) + mean(ms_r1)) / 16 if (ms_r1 and ms_plain) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32" if _lib.umma_enabled() else "f32", "data": "synthetic",
         "config": {"workload": workload_name(B, S), "global_batch": B * world, "parallelism": f"dp{world}",
-                   "r1_iterations_in_window": r1_in_window, "cuda_graphs": not args.no_graphs,
+                   "r1_iterations_in_window": r1_in_window, "ms_per_step_plain": mean(ms_plain), "ms_per_step_r1": mean(ms_r1),
+                   "ms_per_step_amortised_16": amort, "cuda_graphs": not args.no_graphs,
                    "second_backward": "Ex parameters only (pruned)" if args.prune_dead_backward else "full graph, as train.py:214-216",
                    "l2": "activations of one step are tens of GB, far larger than the 126 MB L2; no explicit flush",
                    "est_tflops": FLOP_PER_IMAGE_STEP * value / 1e12 if S == 256 else None},
         "clocks": clocks, "gpu_launches": launches,
     }
     if not args.no_e2e:
-        ms2, _, _, d2h = timed(True)
+        ms2, _, _, d2h, _ = timed(True)
         line["e2e"] = {"value": B * world * args.steps / (ms2 * 1e-3), "unit": UNIT,
                        "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": d2h,
                        "api": "ideas_b200.train_step.Trainer.step"}
@@ -365,10 +508,15 @@ def run_ours(args):
             peaks, kind = load_peaks()
             if not args.no_roofline:
                 line.update(roofline_sections(peaks, kind))
+            if not args.no_library_baseline:
+                sys.path.insert(0, os.path.join(ROOT, "scripts"))
+                import library_baseline
+                line["library_baseline"] = library_baseline.run(line)
             if not args.no_cpu_baseline:
-                t, cores, _ = cpu_reference_step_time(S, 1, 0)
-                line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port",
-                                        "sample": f"1 train iteration on 1 image {S}x{S} (oracle port of train.py:33-221), {t:.1f} s"}
+                t, cores, n, kind = cpu_reference_step_time(S, 2, 0, budget_s=30.0)
+                line["cpu_baseline"] = {"value": CPU_BATCH / t, "unit": UNIT, "cores": cores, "kind": kind,
+                                        "sample": f"{n} train iteration(s) on {CPU_BATCH} images {S}x{S} "
+                                                  f"({'unmodified reference' if kind == 'reference' else 'oracle port of train.py:33-221'}), {t:.1f} s each"}
         print(json.dumps(line), flush=True)
     if world > 1:
         # The captured graphs hold NCCL work: tearing the communicator down while they are alive can block at
@@ -383,7 +531,9 @@ def run_ours(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.case:
+        run_case(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

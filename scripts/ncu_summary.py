@@ -24,15 +24,38 @@ KEYS = [
     ("smsp__cycles_active.avg", "SM active cycles"),
     ("sm__cycles_elapsed.max", "elapsed cycles"),
 ]
-for path in sys.argv[1:]:
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
+import json
+import os
+
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+args = sys.argv[1:]
+traffic_path = None
+if args and args[0] == "--traffic":
+    traffic_path, args = args[1], args[2:]
+traffic = {}
+if traffic_path and os.path.exists(traffic_path):
+    traffic = json.load(open(traffic_path))
+for path in args:
+    if path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(io.StringIO(raw)) if len(r) > 5]
     hdr, units, vals = rows[0], rows[1], rows[2]
     name = vals[hdr.index("Kernel Name")]
     print(f"## {path}\nkernel: {name}")
+    got = {}
     for key, label in KEYS:
         for h, u, v in zip(hdr, units, vals):
             if h == key or h.endswith("." + key):
                 print(f"  {label:24s} {v} {u}")
+                got[key] = (v, u)
                 break
     print()
+    if traffic_path and "dram__bytes_read.sum" in got and "dram__bytes_write.sum" in got:
+        tot = sum(float(got[k][0].replace(",", "")) * UNIT.get(got[k][1], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        case = os.path.basename(path).split(".")[0].split("_", 1)[1]
+        traffic[case] = {"dram_bytes": int(tot), "kernel": name[:80],
+                         "source": f"profiles/{os.path.basename(path).split('.')[0]}.raw.csv (ncu --set full, one launch)"}
+if traffic_path:
+    json.dump(traffic, open(traffic_path, "w"), indent=1)

@@ -1,0 +1,76 @@
+"""Full-width parity: the BASELINE cfg-3 layer against the CPU oracle, and the weight gradient at
+a reduction length of >= 1 M pixels against fp64.
+
+* cfg 3 at B = 2: ModulatedConv2d(512, 512, 3, style_dim 2048) + FusedLeakyReLU on x (2, 512, 64, 64), forward and
+  all gradients (x, style, W, modulation weight / bias, activation bias) vs oracle.functional.styled_conv
+  (stylegan2/model.py:236-277, :343-377).  Every tcgen05 kernel of the layer runs at its production width.
+* wgrad at K = B*H*W = 1 048 576 (SURVEY.md §7 hard part 2): tf32 products accumulated in fp32 over a million
+  pixels and merged with red.global.add -- error vs an fp64 reference measured and bounded.
+"""
+import pytest
+import torch
+
+import tolerances as T
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg3_layer_full_width_vs_oracle():
+    from ideas_b200.stylegan2 import model as M
+    from oracle import functional as O
+    torch.manual_seed(0)
+    B, C, H, SD = 2, 512, 64, 2048
+    m = M.StyledConv_without_noise(C, C, 3, SD)
+    m.activate.bias.data.normal_()
+    x = torch.randn(B, C, H, H)
+    st = torch.rand(B, SD) * 2 - 1
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items() if "kernel" not in k}
+    xr, sr = x.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    want = O.styled_conv(xr, sr, sd["conv.weight"], sd["conv.modulation.weight"], sd["conv.modulation.bias"],
+                         sd["activate.bias"])
+    gy = torch.randn_like(want)
+    names = ["conv.weight", "conv.modulation.weight", "conv.modulation.bias", "activate.bias"]
+    wg = torch.autograd.grad(want, [xr, sr] + [sd[n] for n in names], gy)
+    m = m.cuda()
+    xc, sc = x.cuda().requires_grad_(True), st.cuda().requires_grad_(True)
+    got = m(xc, sc)
+    params = dict(m.named_parameters())
+    gg = torch.autograd.grad(got, [xc, sc] + [params[n] for n in names], gy.cuda())
+    e = T.record("cfg3_B2.out.rel", T.rel(got, want), T.OUT["tf32"])
+    assert e <= T.OUT["tf32"], e
+    for a, b, name in zip(gg, wg, ["dx", "dstyle"] + ["d" + n for n in names]):
+        T.record(f"cfg3_B2.{name}.rel_l2", T.rel_l2(a, b))
+        if a.numel() >= 10000:
+            T.record(f"cfg3_B2.{name}.q95", T.rel_q(a, b))
+        T.assert_grad_through_act(a, b, "tf32", name)
+
+
+def test_wgrad_million_pixel_reduction_vs_fp64():
+    from ideas_b200 import _lib
+    from ideas_b200._tensor import ptr, stream_ptr
+    N, C, K, H = 16, 64, 128, 256                          # N*H*W = 1 048 576 pixels reduced into each of 9*128*64 sums
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(N, H, H, C, device="cuda", generator=g)
+    dy = torch.randn(N, H, H, K, device="cuda", generator=g)
+    dwp = torch.zeros(9, K, C, device="cuda")
+    _lib.call("ideas_conv2d_wgrad", ptr(dwp), ptr(x), ptr(dy), ptr(None), ptr(None), N, H, H, C, K, 3, 3, 1, 1, H, H,
+              _lib.IMPL_UMMA, stream_ptr(x))
+    # fp64 reference on a subset of output channels (the full fp64 conv-weight gradient would take minutes)
+    ks = [0, 37, 127]
+    xn = x.permute(0, 3, 1, 2).double()
+    ref = torch.zeros(9, len(ks), C, dtype=torch.float64, device="cuda")
+    xp = torch.nn.functional.pad(xn, [1, 1, 1, 1])
+    for j, k in enumerate(ks):
+        gk = dy[..., k].double()                              # (N, H, W)
+        for a in range(3):
+            for b in range(3):
+                ref[a * 3 + b, j] = torch.einsum("nchw,nhw->c", xp[:, :, a:a + H, b:b + H], gk)
+    got = dwp[:, ks, :].double()
+    scale = ref.abs().max()
+    err = float((got - ref).abs().max() / scale)
+    T.record("wgrad_K1M.max_abs_over_max", err, 2e-3)
+    rms = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    T.record("wgrad_K1M.rel_rms", rms, 1e-3)
+    # tf32 rounding errors of the 1 M products are independent: the sum's error grows like sqrt(K) * 2^-11 * |x||dy|,
+    # the same scaling as the sum itself for random data, so the relative error stays at the single-product level
+    assert err <= 2e-3 and rms <= 1e-3, (err, rms)

@@ -16,7 +16,8 @@ from ctypes import c_float, c_int, c_int64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "lib", "libideas_b200.so")
-SOURCES = ["bias_act.cu", "upfirdn2d.cu", "conv_simt.cu", "conv_umma.cu", "conv_pointwise.cu", "elementwise.cu", "bits.cu"]
+SOURCES = ["bias_act.cu", "upfirdn2d.cu", "conv_simt.cu", "conv_umma.cu", "conv_pointwise.cu", "elementwise.cu", "bits.cu",
+           "linear.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -42,11 +43,13 @@ _PROTOTYPES = {
     "ideas_unpack_weight_grad": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P],
     "ideas_repack_dgrad": [_P, _P, c_int, c_int, c_int, _P],
     "ideas_conv2d_forward": [_P] * 6 + [c_int] * 9 + [c_int, c_float, c_float, c_int, _P],
+    "ideas_conv2d_forward_res": [_P] * 7 + [c_float] + [c_int] * 9 + [c_int, c_float, c_float, c_int, _P],
     "ideas_conv2d_dgrad": [_P] * 6 + [c_int] * 11 + [c_int, c_float, c_float, c_int, _P],
     "ideas_conv2d_wgrad": [_P] * 5 + [c_int] * 11 + [c_int, _P],
     "ideas_scale_channels": [_P, _P, _P, c_int, c_int64, c_int, _P],
     "ideas_channel_dot": [_P, _P, _P, _P, _P, c_int, c_int64, c_int, _P],
     "ideas_add_scale": [_P, _P, _P, c_float, c_int64, _P],
+    "ideas_gemm_nt": [_P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int, _P],
     "ideas_reflect_pad2d": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P],
     "ideas_patchify_forward": [_P, _P, _P] + [c_int] * 7 + [_P],
     "ideas_patchify_backward": [_P, _P, _P] + [c_int] * 7 + [_P],

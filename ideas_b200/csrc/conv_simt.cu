@@ -17,7 +17,8 @@ namespace ideas {
 
 // implemented in conv_umma.cu; return IDEAS_ERR_UNSUPPORTED when the shape does not qualify
 int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
-                     const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run);
+                     const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run,
+                     const float* residual = nullptr, float res_scale = 1.f);
 int umma_wgrad_launch(const ConvGeom& g, float* dwp, const float* src, const float* dy, cudaStream_t st, bool dry_run);
 // implemented in conv_pointwise.cu: 1x1 convs with <= 4 channels on one side (HBM-bound streaming kernels)
 int pointwise_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* bias, int act,
@@ -32,6 +33,8 @@ struct ConvArgs {
   const float* in_scale;
   const float* out_scale;
   const float* bias;
+  const float* residual;   // dst-shaped, merged after the activation: (act(..) + residual) * res_scale
+  float res_scale;
   int act;
   float alpha, gain;
   int64_t M;
@@ -152,7 +155,8 @@ __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const __grid_const
     const int64_t t = mm / g.QW;
     const int oy = (int)(t % g.QH);
     const int nn = (int)(t / g.QH);
-    float* dp = a.dst + (((int64_t)nn * g.OH + (oy * g.o_s + g.o_py)) * g.OW + (ox * g.o_s + g.o_px)) * g.OC;
+    const int64_t poff = (((int64_t)nn * g.OH + (oy * g.o_s + g.o_py)) * g.OW + (ox * g.o_s + g.o_px)) * g.OC;
+    float* dp = a.dst + poff;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const __grid_const
         if (a.out_scale) r *= __ldg(a.out_scale + (int64_t)nn * g.OC + k);
         if (a.bias) r += __ldg(a.bias + k);
         if (a.act == IDEAS_ACT_LRELU) r = lrelu(r, a.alpha) * a.gain;
+        if (a.residual) r = (r + __ldg(a.residual + poff + k)) * a.res_scale;
       }
       v[j] = r;
     }
@@ -340,9 +345,11 @@ __global__ void __launch_bounds__(256) repack_dgrad_kernel(float* __restrict__ d
 }
 
 static int launch_simt(const ConvGeom& g, float* dst, const float* src, const float* w, const float* in_scale,
-                       const float* out_scale, const float* bias, int act, float alpha, float gain, cudaStream_t st) {
+                       const float* out_scale, const float* bias, int act, float alpha, float gain, cudaStream_t st,
+                       const float* residual = nullptr, float res_scale = 1.f) {
   ConvArgs a;
   a.g = g; a.src = src; a.w = w; a.dst = dst; a.in_scale = in_scale; a.out_scale = out_scale; a.bias = bias;
+  a.residual = residual; a.res_scale = res_scale;
   a.act = act; a.alpha = alpha; a.gain = gain;
   a.M = (int64_t)g.N * g.QH * g.QW;
   if (a.M == 0 || g.OC == 0) return IDEAS_OK;
@@ -408,6 +415,14 @@ extern "C" int ideas_conv2d_forward(float* y, const float* x, const float* wp, c
                                     const float* out_scale, const float* bias, int N, int H, int W, int C, int K,
                                     int kh, int kw, int stride, int pad, int act, float alpha, float gain, int impl,
                                     void* stream) {
+  return ideas_conv2d_forward_res(y, x, wp, in_scale, out_scale, bias, nullptr, 1.f, N, H, W, C, K, kh, kw, stride, pad,
+                                  act, alpha, gain, impl, stream);
+}
+
+extern "C" int ideas_conv2d_forward_res(float* y, const float* x, const float* wp, const float* in_scale,
+                                        const float* out_scale, const float* bias, const float* residual,
+                                        float res_scale, int N, int H, int W, int C, int K, int kh, int kw, int stride,
+                                        int pad, int act, float alpha, float gain, int impl, void* stream) {
   int rc = check_conv_args("conv2d_forward", N, H, W, C, K, kh, kw, stride, pad);
   if (rc) return rc;
   IDEAS_REQUIRE(H + 2 * pad >= kh && W + 2 * pad >= kw, "conv2d_forward: kernel larger than padded input");
@@ -416,19 +431,19 @@ extern "C" int ideas_conv2d_forward(float* y, const float* x, const float* wp, c
   IDEAS_REQUIRE(y && x && wp, "conv2d_forward: null pointer");
   const ConvGeom g = geom_forward(N, H, W, C, K, kh, kw, stride, pad, OH, OW);
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == IDEAS_IMPL_AUTO && !in_scale && !out_scale) {
+  if (impl == IDEAS_IMPL_AUTO && !in_scale && !out_scale && !residual) {
     rc = pointwise_conv_launch(g, y, x, wp, bias, act, alpha, gain, st);
     if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
   }
   if (umma_wanted(impl) && !in_scale) {
-    rc = umma_conv_launch(g, y, x, wp, out_scale, bias, act, alpha, gain, st, false);
+    rc = umma_conv_launch(g, y, x, wp, out_scale, bias, act, alpha, gain, st, false, residual, res_scale);
     if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
   }
   if (impl == IDEAS_IMPL_UMMA) {
     set_error("conv2d_forward: shape not eligible for the tcgen05 path (or in_scale given)");
     return IDEAS_ERR_UNSUPPORTED;
   }
-  return launch_simt(g, y, x, wp, in_scale, out_scale, bias, act, alpha, gain, st);
+  return launch_simt(g, y, x, wp, in_scale, out_scale, bias, act, alpha, gain, st, residual, res_scale);
 }
 
 extern "C" int ideas_conv2d_dgrad(float* dx, const float* dy, const float* wpt, const float* in_scale,

@@ -57,6 +57,8 @@ struct alignas(64) FwdParams {
   float* dst;
   const float* out_scale;
   const float* bias;
+  const float* residual;
+  float res_scale;
   int N, QH, QW;
   int OH, OW, OC;
   int o_s, o_py, o_px;
@@ -176,8 +178,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
       const bool valid = sub_ok[j] && n < p.N && qy < p.QH && qx < p.QW;
       float* dp = nullptr;
       const float* os = nullptr;
+      const float* rp = nullptr;
       if (valid) {
-        dp = p.dst + (((int64_t)n * p.OH + (qy * p.o_s + p.o_py)) * p.OW + (qx * p.o_s + p.o_px)) * p.OC + k0;
+        const int64_t off = (((int64_t)n * p.OH + (qy * p.o_s + p.o_py)) * p.OW + (qx * p.o_s + p.o_px)) * p.OC + k0;
+        dp = p.dst + off;
+        if (p.residual) rp = p.residual + off;
         if (p.out_scale) os = p.out_scale + (int64_t)n * p.OC + k0;
       }
       for (int ch = 0; ch < BN / 32; ++ch) {
@@ -198,6 +203,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
             if (p.act == IDEAS_ACT_LRELU) {
               r.x = lrelu(r.x, p.alpha) * p.gain; r.y = lrelu(r.y, p.alpha) * p.gain;
               r.z = lrelu(r.z, p.alpha) * p.gain; r.w = lrelu(r.w, p.alpha) * p.gain;
+            }
+            if (rp) {
+              const float4 q = ld_stream4(rp + ch * 32 + i);
+              const float rs = p.res_scale;
+              r.x = (r.x + q.x) * rs; r.y = (r.y + q.y) * rs; r.z = (r.z + q.z) * rs; r.w = (r.w + q.w) * rs;
             }
             *reinterpret_cast<float4*>(dp + ch * 32 + i) = r;
           }
@@ -661,10 +671,368 @@ int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
   return IDEAS_OK;
 }
 
+
+// ==========================================================================================
+// Pixel-major halo kernel ("pmh"): the halo-reuse idea with the GEMM roles of the forward-form kernel,
+//   D[pixel, k] = sum_{tap, c} X[pixel + tap, c] * Wp[tap][k][c]     (M = 128 slab positions, N = OCT output channels)
+// The halo kernel above puts the output channels on the 128 TMEM lanes: with 32 or 64 of them half or three
+// quarters of every MMA is spent on zero rows (tcgen05 costs max(M,128)*N/256 clk whatever M is), and its
+// epilogue (lane = channel) stores 4 bytes per thread per instruction.  Here the A operand is the halo'd
+// activation slab itself: sub-tile s of tap (dy,dx) is the 128 CONSECUTIVE slab rows starting at
+// s*128 + dy*bwp + dx (address-based swizzle, as above), so accumulator row m is slab position m = y*bwp + x,
+// N = OCT in {32, 64, 128} is exactly the layer's width, and the epilogue is pixel-major: one thread = one pixel,
+// 32 consecutive channels per tcgen05.ld, 128-bit NHWC stores.  Slab positions in the halo columns (x >= bw)
+// and past the tile produce rows that are dropped; rows read past the TMA box only feed such rows (row m of D
+// depends on row m of A alone).  Persistent, two TMEM buffers of nsub accumulators (nsub*OCT <= 256 columns
+// each), weight tiles and slabs in TMA rings, epilogue of item i under the MMAs of item i+1 -- as above.
+// The epilogue also takes a residual operand: out = (act(d*acc + bias) + residual) * res_scale, the merge
+// (out + skip)/sqrt(2) of the residual blocks (models.py:178,227) without its own pass over HBM.
+// ==========================================================================================
+constexpr int kPmhMaxWStages = 16;
+constexpr int kPmhThreads = 352;
+constexpr int kPmhEpiWarps = 8;
+constexpr uint32_t kPmhSmemBudget = 224 * 1024;
+
+std::atomic<int> g_pmh_mode{1};               // 0 = never, 1 = heuristic, 2 = whenever eligible
+
+struct alignas(64) PmhParams {
+  CUtensorMap src;
+  CUtensorMap w;
+  float* dst;
+  const float* out_scale;
+  const float* bias;
+  const float* residual;
+  float res_scale;
+  int N, QH, QW;
+  int OH, OW, OC;
+  int o_s, o_py, o_px;
+  int bw, bwp, bh, nsub, oct;
+  int box_rows;
+  int x_org, y_org;
+  int tiles_x, tiles_y, ktiles, items;
+  int ntaps, csteps;
+  int x_stages, w_stages;
+  uint32_t x_slot_bytes, x_tx_bytes, w_bytes;
+  int act;
+  float alpha, gain;
+  TapH taps[kMaxTaps];
+};
+
+__global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __grid_constant__ PmhParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t wfull[kPmhMaxWStages];
+  __shared__ __align__(8) uint64_t wempty[kPmhMaxWStages];
+  __shared__ __align__(8) uint64_t xfull[3];
+  __shared__ __align__(8) uint64_t xempty[3];
+  __shared__ __align__(8) uint64_t tfull[2];
+  __shared__ __align__(8) uint64_t tempty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t wring = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t xring = wring + p.w_stages * p.w_bytes;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kPmhMaxWStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&wfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&wempty[s]), 1);
+    }
+    for (int s = 0; s < 3; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&xfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&xempty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty[s]), kPmhEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+#define IDEAS_PMH_DECODE(item)                          \
+  const int kt = (item) % p.ktiles;                     \
+  const int pt = (item) / p.ktiles;                     \
+  const int bx = pt % p.tiles_x;                        \
+  const int tt = pt / p.tiles_x;                        \
+  const int qx0 = bx * p.bw;                            \
+  const int qy0 = (tt % p.tiles_y) * p.bh;              \
+  const int n = tt / p.tiles_y;                         \
+  const int k0 = kt * p.oct;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== weight tiles: one (32-channel step, tap) per ring slot, OCT rows of 128 B =====
+      ptx::tma_prefetch_desc(&p.w);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int k0 = (item % p.ktiles) * p.oct;
+        for (int cs = 0; cs < p.csteps; ++cs)
+          for (int t = 0; t < p.ntaps; ++t) {
+            ptx::mbar_wait(ptx::smem_u32(&wempty[stage]), phase ^ 1u);
+            const uint32_t fb = ptx::smem_u32(&wfull[stage]);
+            ptx::mbar_arrive_expect_tx(fb, p.w_bytes);
+            ptx::tma_load_3d(wring + stage * p.w_bytes, &p.w, fb, cs * kBlockK, k0, p.taps[t].widx);
+            if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== activation slabs: one halo'd box per 32-channel step =====
+      ptx::tma_prefetch_desc(&p.src);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        IDEAS_PMH_DECODE(item)
+        (void)k0;
+        for (int cs = 0; cs < p.csteps; ++cs) {
+          ptx::mbar_wait(ptx::smem_u32(&xempty[stage]), phase ^ 1u);
+          const uint32_t fb = ptx::smem_u32(&xfull[stage]);
+          ptx::mbar_arrive_expect_tx(fb, p.x_tx_bytes);
+          ptx::tma_load_4d(xring + stage * p.x_slot_bytes, &p.src, fb, cs * kBlockK, qx0 + p.x_org, qy0 + p.y_org, n);
+          if (++stage == p.x_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ptx::idesc_tf32(128, p.oct, 0, 0);
+      int ws = 0, xs = 0;
+      uint32_t wphase = 0, xphase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty[buf]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * 256;
+        for (int cs = 0; cs < p.csteps; ++cs) {
+          ptx::mbar_wait(ptx::smem_u32(&xfull[xs]), xphase);
+          const uint32_t xa = xring + xs * p.x_slot_bytes;
+          for (int t = 0; t < p.ntaps; ++t) {
+            ptx::mbar_wait(ptx::smem_u32(&wfull[ws]), wphase);
+            ptx::tc_fence_after();
+            const uint64_t bdesc = ptx::smem_desc_sw128(wring + ws * p.w_bytes, 16, 1024);
+            const uint32_t a0 = xa + (uint32_t)p.taps[t].rowoff * 128u;
+            for (int s = 0; s < p.nsub; ++s) {
+              const uint64_t adesc = ptx::smem_desc_sw128(a0 + (uint32_t)s * (128u * 128u), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                ptx::mma_tf32(acc + s * p.oct, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cs | t | k) != 0));
+            }
+            ptx::mma_commit(ptx::smem_u32(&wempty[ws]));
+            if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
+          }
+          ptx::mma_commit(ptx::smem_u32(&xempty[xs]));
+          if (++xs == p.x_stages) { xs = 0; xphase ^= 1u; }
+        }
+        ptx::mma_commit(ptx::smem_u32(&tfull[buf]));
+      }
+    }
+  } else {
+    // ===== epilogue: warps 3..10; TMEM lane quarter = warp % 4 (lane = slab position inside the sub-tile); the two
+    // warps of a quarter take alternate (sub-tile, 32-channel chunk) units =====
+    const int quarter = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int cpt = p.oct >> 5;
+    const int units = p.nsub * cpt;
+    const bool lrelu_on = p.act == IDEAS_ACT_LRELU;
+    const float alpha = p.alpha, gain = lrelu_on ? p.gain : 1.f;
+    const float rs = p.res_scale;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      IDEAS_PMH_DECODE(item)
+      const int buf = it & 1;
+      const int xlim = min(p.bw, p.QW - qx0);
+      const int ylim = min(p.bh, p.QH - qy0);
+      const int64_t base = (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + k0;
+      const float* osn = p.out_scale ? p.out_scale + (int64_t)n * p.OC + k0 : nullptr;
+      ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      for (int u = half; u < units; u += 2) {
+        const int sub = u / cpt;
+        const int ch = u - sub * cpt;
+        const int m = sub * 128 + quarter * 32 + lane;
+        const int y = m / p.bwp;
+        const int x = m - y * p.bwp;
+        float v[32];
+        ptx::tmem_ld_32x32(acc + (uint32_t)(sub * p.oct + ch * 32), v);
+        if (x < xlim && y < ylim) {
+          const int64_t off = base + ((int64_t)y * p.o_s * p.OW + (int64_t)x * p.o_s) * p.OC + ch * 32;
+          float* dp = p.dst + off;
+          const float* rp = p.residual ? p.residual + off : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (osn) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(osn + ch * 32 + i));
+              r.x *= s4.x; r.y *= s4.y; r.z *= s4.z; r.w *= s4.w;
+            }
+            if (p.bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + i));
+              r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
+            }
+            if (lrelu_on) {
+              r.x = lrelu(r.x, alpha) * gain; r.y = lrelu(r.y, alpha) * gain;
+              r.z = lrelu(r.z, alpha) * gain; r.w = lrelu(r.w, alpha) * gain;
+            }
+            if (rp) {
+              const float4 q = ld_stream4(rp + i);
+              r.x = (r.x + q.x) * rs; r.y = (r.y + q.y) * rs; r.z = (r.z + q.z) * rs; r.w = (r.w + q.w) * rs;
+            }
+            *reinterpret_cast<float4*>(dp + i) = r;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ptx::smem_u32(&tempty[buf]));
+    }
+  }
+#undef IDEAS_PMH_DECODE
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct PmhTile {
+  int bw, bwp, bh, nsub, tiles_x, tiles_y, w_stages;
+  uint32_t slot_bytes;
+  double cycles;
+};
+
+// (bw, bh) minimising modelled time per image = tiles * max(MMA cycles, L2-feed cycles) per 32-channel step
+bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile* out) {
+  struct Key { int a, b, c, d, e, f; bool operator<(const Key& o) const { return memcmp(this, &o, sizeof(Key)) < 0; } };
+  static std::mutex mu;
+  static std::map<Key, PmhTile> cache;
+  const Key key{QW, QH, hx, hy, ntaps, oct};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return it->second.bw > 0; }
+  }
+  PmhTile best{};
+  best.bw = 0; best.cycles = 1e300;
+  const uint32_t w_bytes = (uint32_t)oct * 128u;
+  const int max_sub = 256 / oct;
+  for (int bw = (QW < 4 ? QW : 4); bw <= QW && bw + hx <= 256; ++bw) {
+    const int bwp = bw + hx;
+    for (int bh = 1; bh <= QH && bh + hy <= 256; ++bh) {
+      const int nsub = ceil_div(bh * bwp, 128);
+      if (nsub > max_sub) break;
+      const uint32_t slot = (uint32_t)((nsub * 128 + hy * bwp + hx) * 128 + 1023) & ~1023u;
+      if (2 * slot + 4 * w_bytes > kPmhSmemBudget) break;
+      const int tx = ceil_div(QW, bw), ty = ceil_div(QH, bh);
+      const double mma = (double)ntaps * nsub * 4 * (oct / 2.0);
+      const double l2 = ((double)ntaps * w_bytes + (double)(bh + hy) * bwp * 128) / 48.0;
+      const double cyc = (double)tx * ty * ((mma > l2 ? mma : l2) + 24.0);
+      if (cyc < best.cycles) {
+        best.bw = bw; best.bwp = bwp; best.bh = bh; best.nsub = nsub; best.tiles_x = tx; best.tiles_y = ty;
+        best.slot_bytes = slot; best.cycles = cyc;
+        const int ws = (int)((kPmhSmemBudget - 2 * slot) / w_bytes);
+        best.w_stages = ws > kPmhMaxWStages ? kPmhMaxWStages : ws;
+      }
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = best;
+  }
+  *out = best;
+  return best.bw > 0;
+}
+
+int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
+                    const float* bias, const float* residual, float res_scale, int act, float alpha, float gain,
+                    cudaStream_t st) {
+  const int mode = g_pmh_mode.load();
+  if (mode == 0 || g.i_s != 1 || g.ntaps < 1) return IDEAS_ERR_UNSUPPORTED;
+  if (g.QW < 4 || g.QH < 1) return IDEAS_ERR_UNSUPPORTED;
+  int min_dx = 1 << 30, max_dx = -(1 << 30), min_dy = 1 << 30, max_dy = -(1 << 30), max_widx = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    min_dx = g.taps[t].dx < min_dx ? g.taps[t].dx : min_dx; max_dx = g.taps[t].dx > max_dx ? g.taps[t].dx : max_dx;
+    min_dy = g.taps[t].dy < min_dy ? g.taps[t].dy : min_dy; max_dy = g.taps[t].dy > max_dy ? g.taps[t].dy : max_dy;
+    max_widx = g.taps[t].widx > max_widx ? g.taps[t].widx : max_widx;
+  }
+  const int hx = max_dx - min_dx, hy = max_dy - min_dy;
+  if (hx > 8 || hy > 8) return IDEAS_ERR_UNSUPPORTED;
+  const int oct = (g.OC % 128 == 0) ? 128 : (g.OC % 64 == 0) ? 64 : 32;
+  if (mode == 1) {
+    // where it wins (scripts/kernels_microbench.py, IDEAS_OPTS pmh=0 vs 2): layers whose output width is not a
+    // multiple of 128 -- 32 and 64 output channels, i.e. the first blocks of E / Dco / Dreal and the data gradients
+    // of their 64 -> 128 / 32 -> 64 convolutions -- and every residual-merging epilogue
+    if (oct == 128 && !(residual && g.IC <= 128)) return IDEAS_ERR_UNSUPPORTED;
+    if (g.IC > 128) return IDEAS_ERR_UNSUPPORTED;
+  }
+  PmhTile tile;
+  if (!choose_pmh_tile(g.QW, g.QH, hx, hy, g.ntaps, oct, &tile)) return IDEAS_ERR_UNSUPPORTED;
+
+  PmhParams p;
+  p.dst = dst; p.out_scale = out_scale; p.bias = bias; p.residual = residual; p.res_scale = res_scale;
+  p.N = g.N; p.QH = g.QH; p.QW = g.QW; p.OH = g.OH; p.OW = g.OW; p.OC = g.OC;
+  p.o_s = g.o_s; p.o_py = g.o_py; p.o_px = g.o_px;
+  p.bw = tile.bw; p.bwp = tile.bwp; p.bh = tile.bh; p.nsub = tile.nsub; p.oct = oct;
+  p.box_rows = tile.bh + hy;
+  p.x_org = min_dx; p.y_org = min_dy;
+  p.tiles_x = tile.tiles_x; p.tiles_y = tile.tiles_y;
+  p.ktiles = g.OC / oct;
+  const int64_t items = (int64_t)g.N * p.tiles_y * p.tiles_x * p.ktiles;
+  if (items > (1ll << 30)) return IDEAS_ERR_UNSUPPORTED;
+  p.items = (int)items;
+  p.ntaps = g.ntaps; p.csteps = g.IC / kBlockK;
+  p.x_stages = 2;
+  p.w_stages = tile.w_stages;
+  p.x_slot_bytes = tile.slot_bytes;
+  p.x_tx_bytes = (uint32_t)(p.box_rows * p.bwp * 128);
+  p.w_bytes = (uint32_t)oct * 128u;
+  p.act = act; p.alpha = alpha; p.gain = gain;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.taps[t].rowoff = (g.taps[t].dy - min_dy) * p.bwp + (g.taps[t].dx - min_dx);
+    p.taps[t].widx = g.taps[t].widx;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)g.IC, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)g.IC * 4, (uint64_t)g.IW * g.IC * 4, (uint64_t)g.IH * g.IW * g.IC * 4};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.bwp, (uint32_t)p.box_rows, 1u};
+    int rc = encode_map(&p.src, src, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)g.IC, (uint64_t)g.OC, (uint64_t)(max_widx + 1)};
+    const uint64_t strides[2] = {(uint64_t)g.IC * 4, (uint64_t)g.OC * g.IC * 4};
+    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)oct, 1u};
+    int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
+    if (rc) return rc;
+  }
+  const uint32_t smem = p.w_stages * p.w_bytes + p.x_stages * p.x_slot_bytes + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_umma_pmh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kPmhSmemBudget + 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_pmh: cudaFuncSetAttribute");
+  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  conv_umma_pmh_kernel<<<grid, kPmhThreads, smem, st>>>(p);
+  IDEAS_CHECK_LAUNCH("conv_umma_pmh");
+  return IDEAS_OK;
+}
+
 }  // namespace
 
 int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
-                     const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run) {
+                     const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run,
+                     const float* residual, float res_scale) {
   // ---- eligibility
   if (g.IC % 32 || g.OC % 32 || g.ntaps < 1) return IDEAS_ERR_UNSUPPORTED;
   if (g.i_s != 1 && g.i_s != 2) return IDEAS_ERR_UNSUPPORTED;
@@ -673,14 +1041,19 @@ int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
       (bias && !aligned16(bias)))
     return IDEAS_ERR_UNSUPPORTED;
   if (g.IH > 32767 || g.IW > 32767) return IDEAS_ERR_UNSUPPORTED;
+  if (residual && !aligned16(residual)) return IDEAS_ERR_UNSUPPORTED;
   if (dry_run) return IDEAS_OK;
   {
+    const int rc = pmh_conv_launch(g, dst, src, w, out_scale, bias, residual, res_scale, act, alpha, gain, st);
+    if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
+  }
+  if (!residual) {      // the channel-major halo kernel has no residual operand; both pixel-major kernels do
     const int rc = halo_conv_launch(g, dst, src, w, out_scale, bias, act, alpha, gain, st);
     if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
   }
 
   FwdParams p;
-  p.dst = dst; p.out_scale = out_scale; p.bias = bias;
+  p.dst = dst; p.out_scale = out_scale; p.bias = bias; p.residual = residual; p.res_scale = res_scale;
   p.N = g.N; p.QH = g.QH; p.QW = g.QW; p.OH = g.OH; p.OW = g.OW; p.OC = g.OC;
   p.o_s = g.o_s; p.o_py = g.o_py; p.o_px = g.o_px;
   p.act = act; p.alpha = alpha; p.gain = gain;
@@ -1101,6 +1474,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "halo")) {
     ideas::g_halo_mode.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pmh")) {
+    ideas::g_pmh_mode.store(value);
     return IDEAS_OK;
   }
   ideas::set_error("ideas_set_option: unknown option '%s'", name ? name : "(null)");

@@ -22,7 +22,8 @@ from .stylegan2.model import (Blur, EqualConv2d, EqualLinear, ScaledLeakyReLU,
                               StyledConv_without_noise as StyledConv)
 from .stylegan2.op import FusedLeakyReLU, upfirdn2d
 from .stylegan2.op import conv as _ops
-from .stylegan2.op.conv import PackWeight
+from .stylegan2.op.conv import cached, packed_weight
+from .stylegan2.op.linear import matmul_nt
 from .stylegan2.op.elementwise import add_scale, reflect_pad
 
 _INV_SQRT2 = 1.0 / math.sqrt(2.0)
@@ -43,7 +44,7 @@ class EqualConvTranspose2d(nn.Module):
         cin, cout, k, _ = self.weight.shape
         stride = self.stride if stride is None else stride
         # (in, out, k, k) is the OIHW weight of the stride-s conv whose adjoint this layer is
-        wp = PackWeight.apply(self.weight, False, self.scale)
+        wp = packed_weight(self.weight, False, self.scale)
         out = _ops.conv_transpose2d(input, wp, C_out=cout, kh=k, kw=k, stride=stride, pad=self.padding)
         if self.bias is not None:
             out = out + self.bias.view(1, -1, 1, 1)
@@ -155,8 +156,10 @@ class StyledResBlock(nn.Module):
             self.skip = ConvLayer(in_channel, out_channel, 1, upsample=upsample, blur_kernel=blur_kernel,
                                   bias=False, activate=False)
 
-    def forward(self, input, style, noise=None):
-        out = self.conv2(self.conv1(input, style, noise), style, noise)
+    def forward(self, input, style, noise=None, modulation=None):
+        """``modulation``: optional (s1, s2), the outputs of conv1 / conv2's modulation linears."""
+        m1, m2 = modulation if modulation is not None else (None, None)
+        out = self.conv2(self.conv1(input, style, noise, modulation=m1), style, noise, modulation=m2)
         skip = input if self.skip is None else self.skip(input)
         return add_scale(out, skip, _INV_SQRT2)
 
@@ -231,9 +234,25 @@ class Generator(nn.Module):
     def forward(self, structure, texture, noises=None):
         noises = noises if noises is not None else [None] * len(self.layers)
         out = structure
-        for block, noise in zip(self.layers, noises):
-            out = block(out, texture, noise)
+        mods = self.modulations(texture) if texture.is_cuda else [None] * len(self.layers)
+        for block, noise, mod in zip(self.layers, noises, mods):
+            out = block(out, texture, noise, modulation=mod)
         return self.to_rgb(out)
+
+    def modulations(self, texture):
+        """The 16 modulation linears of one call (stylegan2/model.py:226,239: every ModulatedConv2d maps the SAME
+        texture vector through its own EqualLinear) as ONE GEMM on the row-concatenated weights: s_all =
+        texture @ cat(W_l * scale)^T + cat(bias_l), then split per layer."""
+        lins = [conv.conv.modulation for block in self.layers for conv in (block.conv1, block.conv2)]
+
+        def build():
+            return (torch.cat([m.effective_weight() for m in lins], 0),
+                    torch.cat([m.bias * m.lr_mul for m in lins], 0))
+
+        w_all, b_all = cached(lins[0].weight, ("G.modulations", tuple(m.weight._version for m in lins)), build)
+        s_all = matmul_nt(texture, w_all) + b_all
+        parts = torch.split(s_all, [m.weight.shape[0] for m in lins], dim=1)
+        return [(parts[2 * i], parts[2 * i + 1]) for i in range(len(self.layers))]
 
 
 def _same_res_stack(c_in, widths, c_out, blur_kernel):

@@ -23,7 +23,8 @@ from torch.nn import functional as F
 
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 from .op import conv as _ops
-from .op.conv import Geom, ModConv, ModConvUp, PackWeight
+from .op.conv import Geom, ModConv, ModConvUp, PackWeight, cached, packed_weight
+from .op.linear import matmul_nt
 from .._tensor import nhwc
 
 
@@ -94,7 +95,7 @@ class EqualConv2d(nn.Module):
         module's stride (ConvLayer folds the decimation of a 1x1 stride-2 conv into the preceding blur)."""
         k = self.weight.shape[2]
         stride = self.stride if stride is None else stride
-        wp = PackWeight.apply(self.weight, False, self.scale)
+        wp = packed_weight(self.weight, False, self.scale)
         if activation is not None:
             if self.bias is not None:
                 raise RuntimeError("EqualConv2d: a fused activation brings its own bias")
@@ -108,7 +109,7 @@ class EqualConv2d(nn.Module):
         if self.bias is not None:
             raise RuntimeError("EqualConv2d: a fused activation brings its own bias")
         k = self.weight.shape[2]
-        wp = PackWeight.apply(self.weight, False, self.scale)
+        wp = packed_weight(self.weight, False, self.scale)
         g = Geom.forward(input.shape, self.weight.shape[0], k, k, self.stride, self.padding)
         return _ops.ConvActBlur.apply(input, wp, activation.bias, g, activation.negative_slope, activation.scale,
                                       blur.kernel, tuple(blur.pad))
@@ -127,12 +128,19 @@ class EqualLinear(nn.Module):
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
 
+    def effective_weight(self):
+        """weight * scale as a temporary (shared by the uses of one training iteration): the leaf itself is never
+        saved for backward, which keeps train.py:209-216's second backward after optimizer.step() legal."""
+        return cached(self.weight, "eqlin", lambda: self.weight * self.scale)
+
     def forward(self, input):
-        # the GEMM is a plain library call (cuBLAS through F.linear); bias + leaky ReLU is our kernel
-        w = self.weight * self.scale
+        lead = input.shape[:-1]
+        out = matmul_nt(input.reshape(-1, input.shape[-1]), self.effective_weight())   # hand-written fp32 GEMM
         if self.activation:
-            return fused_leaky_relu(F.linear(input, w), self.bias * self.lr_mul)
-        return F.linear(input, w, bias=None if self.bias is None else self.bias * self.lr_mul)
+            return fused_leaky_relu(out, self.bias * self.lr_mul).reshape(*lead, -1)
+        if self.bias is not None:
+            out = out + self.bias * self.lr_mul
+        return out.reshape(*lead, -1)
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})"
@@ -175,31 +183,36 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def forward(self, input, style, activation: FusedLeakyReLU | None = None):
+    def forward(self, input, style, activation: FusedLeakyReLU | None = None, modulation: torch.Tensor | None = None):
         """Returns the modulated convolution; with ``activation`` the FusedLeakyReLU (bias,
-        slope, gain) is applied inside the same kernels (StyledConv passes its own)."""
+        slope, gain) is applied inside the same kernels (StyledConv passes its own).  ``modulation``: the
+        per-sample channel scales s = self.modulation(style), when the caller has already computed them (the
+        Generator evaluates the modulation linears of all its layers in one GEMM)."""
         k = self.kernel_size
         if input.is_cuda:
             # layout conversion OUTSIDE the autograd nodes below: they save their inputs for the double backward
             # (path-length regularisation), which must stay connected to the caller's graph
             input = nhwc(input)
-        s = self.modulation(style).contiguous()                      # (B, Cin)
-        ws = self.weight[0] * self.scale                             # temp, never the leaf (see op/conv.py)
+        s = (self.modulation(style) if modulation is None else modulation).contiguous()   # (B, Cin)
+        def derived():
+            ws = self.weight[0] * self.scale                         # temp, never the leaf (see op/conv.py)
+            wsq = ws.pow(2).sum(dim=(2, 3)) if self.demodulate else None          # (Cout, Cin)
+            # upsampling branch: (taps, Cin, Cout), the packed weight of the stride-2 conv it is the adjoint of
+            return PackWeight.apply(ws, bool(self.upsample), 1.0), wsq
+
+        wp, wsq = cached(self.weight, "modconv", derived)
         d = None
         if self.demodulate:
-            wsq = ws.pow(2).sum(dim=(2, 3))                          # (Cout, Cin)
             d = torch.rsqrt((s * s) @ wsq.t() + self.eps)            # (B, Cout)
         act = activation is not None
         bias = activation.bias if act else None
         alpha = activation.negative_slope if act else 0.2
         gain = activation.scale if act else 1.0
         if self.upsample:
-            wp = PackWeight.apply(ws, True, 1.0)                     # (taps, Cin, Cout)
             g = Geom.transposed(input.shape, self.out_channel, k, k, 2, 0)
             pad = self.blur.pad
             return ModConvUp.apply(input, s, d, wp, self.blur.kernel, (pad[0], pad[1], pad[0], pad[1]), bias, g,
                                    act, alpha, gain)
-        wp = PackWeight.apply(ws, False, 1.0)                        # (taps, Cout, Cin)
         if self.downsample:
             input = self.blur(input)
             g = Geom.forward(input.shape, self.out_channel, k, k, 2, 0)
@@ -256,8 +269,8 @@ class StyledConv_without_noise(nn.Module):
                                     blur_kernel=blur_kernel, demodulate=demodulate)
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward(self, input, style, noise=None):
-        return self.conv(input, style, activation=self.activate)
+    def forward(self, input, style, noise=None, modulation=None):
+        return self.conv(input, style, activation=self.activate, modulation=modulation)
 
 
 class ToRGB(nn.Module):

@@ -45,6 +45,50 @@ def set_default_impl(impl: int) -> int:
     return old
 
 
+# --------------------------------------------------------------------------- per-step cache of derived weights
+class _StepCache:
+    """Packed weights (and the other tensors derived from a parameter alone) are functions of the parameter, which
+    changes once per optimiser step -- yet a training iteration runs E twice, G and Dreal three to six times.  Inside
+    ``step_scope()`` such tensors are built once per (parameter, version, grad mode) and shared by every use: one
+    PackWeight node per weight and phase, whose gradient autograd accumulates before ONE unpack.  The key carries
+    ``Tensor._version`` (bumped by every in-place optimiser update, also while a CUDA graph is being captured), and
+    the cache is dropped when the scope exits, so nothing derived from stale weights -- or living in a graph's
+    private memory pool -- can be seen outside the iteration that built it."""
+    depth = 0
+    store: dict = {}
+
+
+class step_scope:
+    def __enter__(self):
+        if _StepCache.depth == 0:
+            _StepCache.store = {}
+        _StepCache.depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        _StepCache.depth -= 1
+        if _StepCache.depth == 0:
+            _StepCache.store = {}
+        return False
+
+
+def cached(key: torch.Tensor, tag, build):
+    """``build()`` once per (key tensor, version, autograd mode, tag) inside a step_scope; plain call outside."""
+    if _StepCache.depth == 0:
+        return build()
+    k = (id(key), key._version, bool(key.requires_grad and torch.is_grad_enabled()), tag)
+    hit = _StepCache.store.get(k)
+    if hit is None:
+        hit = (key, build())                 # holding ``key`` keeps id() unique while the entry lives
+        _StepCache.store[k] = hit
+    return hit[1]
+
+
+def packed_weight(w: torch.Tensor, transpose: bool, scale: float):
+    """PackWeight of a parameter, shared across the uses of one training iteration."""
+    return cached(w, ("pack", bool(transpose), float(scale)), lambda: PackWeight.apply(w, transpose, scale))
+
+
 class Geom(NamedTuple):
     """Forward-convolution geometry: x (N,C,H,W) -> y (N,K,OH,OW)."""
     N: int
@@ -82,8 +126,12 @@ def _fwd(x, wp, g: Geom, in_scale=None, out_scale=None, bias=None, act=_lib.ACT_
 
 def _dgrad(dy, wp, g: Geom, in_scale=None, out_scale=None, impl=None):
     """dx (N,C,H,W) = in_scale * conv_transpose(out_scale * dy, w)."""
-    wpt = torch.empty_like(wp)
-    _lib.call("ideas_repack_dgrad", ptr(wpt), ptr(wp), g.K, g.C, g.kh * g.kw, stream_ptr(dy))
+    def repack():
+        t = torch.empty_like(wp)
+        _lib.call("ideas_repack_dgrad", ptr(t), ptr(wp), g.K, g.C, g.kh * g.kw, stream_ptr(dy))
+        return t
+
+    wpt = cached(wp, "dgrad", repack)
     dx = empty_nhwc(g.N, g.C, g.H, g.W, dy)
     _lib.call("ideas_conv2d_dgrad", ptr(dx), ptr(dy), ptr(wpt), ptr(in_scale), ptr(out_scale), ptr(None),
               g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, g.OH, g.OW, _lib.ACT_NONE, 0.2, 1.0,

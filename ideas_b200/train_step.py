@@ -78,8 +78,9 @@ class Trainer:
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
-                 prune_dead_backward: bool = False):
+                 prune_dead_backward: bool = False, batch_generator: bool = True):
         self.args = args
+        self.batch_generator = bool(batch_generator)
         self.device = torch.device(device)
         self.cuda_graphs = bool(cuda_graphs and self.device.type == "cuda")
         # independent sub-graphs of one iteration (Dreal on the real batch, the co-occurrence branch, the
@@ -297,6 +298,22 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------- eager core
     def _step_eager(self, X, r1, late, draws, boxes=None, device_rng=False) -> Dict[str, torch.Tensor]:
+        from .stylegan2.op.conv import step_scope
+        with step_scope():                 # packed weights are built once per optimiser step, not once per call
+            return self._iteration(X, r1, late, draws, boxes, device_rng)
+
+    def _generate3(self, S1, S2, T1, T2):
+        """hat_X1, hat_X2, hat_X3 = G(S1,T1), G(S2,T1), G(S2,T2) (train.py:66-70,154-158) and their concatenation
+        (the argument of Dreal, train.py:73,161).  G is per-sample independent (no batch statistics), so the three
+        calls run as ONE call on the concatenated batch: same values and gradients, a third of the launches, and
+        the 16x16 / 32x32 layers fill the GPU."""
+        if not self.batch_generator:
+            xs = self.nets["G"](S1, T1), self.nets["G"](S2, T1), self.nets["G"](S2, T2)
+            return xs, torch.cat(xs, 0)
+        hat = self.nets["G"](torch.cat((S1, S2, S2), 0), torch.cat((T1, T1, T2), 0))
+        return hat.chunk(3, 0), hat
+
+    def _iteration(self, X, r1, late, draws, boxes, device_rng) -> Dict[str, torch.Tensor]:
         a, t = self.args, self.nets
         H, W = X.shape[2], X.shape[3]
 
@@ -327,8 +344,8 @@ class Trainer:
         S1, T1 = t["E"](X)
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_d")
-        hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
-        fake_pred = t["Dreal"](torch.cat((hat_X1, hat_X2, hat_X3), 0))
+        (hat_X1, hat_X2, hat_X3), hat_all = self._generate3(S1, S2, T1, T2)
+        fake_pred = t["Dreal"](hat_all)
         fake_patch = patchify_image(hat_X2, a.n_crop, crops=fake_boxes)
         self._join(1, real_texture_pred, ref_input, real_patch, ref_patch)
         fake_texture_pred, _ = t["Dco"](fake_patch, ref_input=ref_input)
@@ -365,7 +382,7 @@ class Trainer:
         Z = self._rand_like_Z(X, draws, "Z_g", device_rng)
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_g")
-        hat_X1, hat_X2, hat_X3 = t["G"](S1, T1), t["G"](S2, T1), t["G"](S2, T2)
+        (hat_X1, hat_X2, hat_X3), hat_all = self._generate3(S1, S2, T1, T2)
         fake_boxes = crops("fake_crops_g", a.n_crop)
         ref_boxes = crops("ref_crops_g", a.ref_crop * a.n_crop)
         container = hat_X3 if late else hat_X2
@@ -379,7 +396,7 @@ class Trainer:
             fake_patch_pred, _ = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
             G_texture_loss = g_nonsaturating_loss(fake_patch_pred)
         G_rec_loss = F.l1_loss(hat_X1, X)
-        G_real_loss = g_nonsaturating_loss(t["Dreal"](torch.cat((hat_X1, hat_X2, hat_X3), 0)))
+        G_real_loss = g_nonsaturating_loss(t["Dreal"](hat_all))
         E_dist_loss = g_nonsaturating_loss(t["Ddist"](T1))
         self._join(0, E_stru_loss, Ex_loss)
         self._join(1, G_texture_loss)

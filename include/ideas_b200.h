@@ -151,6 +151,14 @@ int ideas_conv2d_forward(float* y, const float* x, const float* wp,
                          const float* in_scale, const float* out_scale, const float* bias,
                          int N, int H, int W, int C, int K, int kh, int kw, int stride, int pad,
                          int act, float alpha, float gain, int impl, void* stream);
+/* Same, merging a residual after the activation: y = (epilogue(..) + residual) * res_scale, with
+ * `residual` of y's shape (NULL = plain forward).  This is the (out + skip)/sqrt(2) of the residual
+ * blocks (models.py:178,227) done in the convolution's epilogue instead of a pass of its own. */
+int ideas_conv2d_forward_res(float* y, const float* x, const float* wp,
+                             const float* in_scale, const float* out_scale, const float* bias,
+                             const float* residual, float res_scale,
+                             int N, int H, int W, int C, int K, int kh, int kw, int stride, int pad,
+                             int act, float alpha, float gain, int impl, void* stream);
 
 /* Data gradient of the forward above == transposed convolution:
  *   dx[n,iy,ix,c] = in_scale[n,c] * sum_{kh,kw,k} wpt[kh',kw'][c][k] * out_scale[n,k] * dy[n,oy,ox,k]
@@ -180,6 +188,16 @@ int ideas_scale_channels(float* out, const float* x, const float* s, int N, int6
  * `dot` must be zero-initialised by the caller. */
 int ideas_channel_dot(float* dot, float* out, const float* a, const float* b, const float* s,
                       int N, int64_t P, int C, void* stream);
+/* ------------------------------------------------------------------------------------
+ * A6  EqualLinear GEMM (reference: F.linear -> cuBLAS, stylegan2/model.py:151-161), exact fp32 FFMA.
+ *   C[i*ldc + j] = alpha * sum_{r<R} a[i*sa_i + r*sa_r] * b[j*sb_j + r*sb_r]        i < M, j < N
+ * Strided operands make forward (x W^T), input gradient (dY W) and weight gradient (dY^T X) one
+ * kernel.  c_is_zero != 0 promises a zero-initialised C and allows a split reduction merged with
+ * fp32 atomics (long R, few tiles). */
+int ideas_gemm_nt(float* c, const float* a, const float* b, int M, int N, int R,
+                  int64_t sa_i, int64_t sa_r, int64_t sb_j, int64_t sb_r, int64_t ldc,
+                  float alpha, int c_is_zero, void* stream);
+
 /* out = (a + b) * gain   (the residual merge (out+skip)/sqrt(2), models.py:178,227) */
 int ideas_add_scale(float* out, const float* a, const float* b, float gain, int64_t n, void* stream);
 

@@ -73,7 +73,8 @@ def cfg2(batches=(1, 32, 96)):
                                     stream_ptr(x)))
         row["lrelu_fwd_ours_gbs"] = (8.0 * n + 4 * C) / t / 1e9
         gb = torch.zeros(C, device=dev)
-        t = _time(lambda: _lib.call("ideas_bias_act_backward", ptr(ya), ptr(gb), ptr(x), ptr(x), 0.2, 2 ** 0.5, n, 1, C,
+        gy = torch.randn_like(x)
+        t = _time(lambda: _lib.call("ideas_bias_act_backward", ptr(ya), ptr(gb), ptr(gy), ptr(x), 0.2, 2 ** 0.5, n, 1, C,
                                     stream_ptr(x)))
         row["lrelu_bwd_ours_gbs"] = (12.0 * n + 4 * C) / t / 1e9
         if ref:
@@ -82,12 +83,13 @@ def cfg2(batches=(1, 32, 96)):
             row["lrelu_fwd_reference_op_gbs"] = (8.0 * n + 4 * C) / t / 1e9
             # the reference's backward is two passes: the masked gradient (act=3, grad=1) and the bias-grad .sum
             # (fused_act.py:29-38); same algorithmic bytes credited as for ours
-            t = _time(lambda: (ref[0].fused_bias_act(xn, empty, xn, 3, 1, 0.2, 2 ** 0.5).sum(dim=(0, 2, 3))))
+            gyn = torch.randn_like(xn)
+            t = _time(lambda: (ref[0].fused_bias_act(gyn, empty, xn, 3, 1, 0.2, 2 ** 0.5).sum(dim=(0, 2, 3))))
             row["lrelu_bwd_reference_op_gbs"] = (12.0 * n + 4 * C) / t / 1e9
         t = _time(lambda: F.leaky_relu(xn + bias.view(1, -1, 1, 1), 0.2) * 2 ** 0.5)
         row["lrelu_fwd_torch_native_gbs"] = (8.0 * n + 4 * C) / t / 1e9
         out[f"B{B}"] = {kk: round(v, 1) for kk, v in row.items()}
-        del x, xn, ya
+        del x, xn, ya, gy
         torch.cuda.empty_cache()
     return out
 

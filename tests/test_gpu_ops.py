@@ -465,3 +465,46 @@ def test_styled_conv_path_length_second_order(cin, cout, res, up):
             assert rel(a, b) <= 2e-3, (name, rel(a, b))      # gradients through the leaky-ReLU mask: a few flips
     finally:
         CV.set_default_impl(old)
+
+
+# ----------------------------------------------------------------------------------- A6 EqualLinear GEMM
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 5, 7), (32, 512, 2048), (96, 1, 512), (128, 512, 8192), (33, 130, 70)])
+def test_matmul_nt_matches_fp64_any_strides(shape):
+    """ideas_gemm_nt through op/linear.py: exact-fp32 a @ b^T for contiguous, transposed and broadcast operands,
+    including the split reduction (8192 -> 512 head)."""
+    from ideas_b200.stylegan2.op.linear import matmul_nt
+    M, N, R = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, R, device="cuda", generator=g)
+    b = torch.randn(N, R, device="cuda", generator=g)
+    want = (a.double() @ b.double().t())
+    scale = want.abs().max().clamp_min(1e-9)
+    assert float((matmul_nt(a, b).double() - want).abs().max() / scale) <= 2e-6
+    at, bt = a.t().contiguous().t(), b.t().contiguous().t()            # same values, reduction index strided
+    assert float((matmul_nt(at, bt).double() - want).abs().max() / scale) <= 2e-6
+    ones = torch.ones(1, 1, device="cuda").expand(M, R)                # stride-0 operand (gradient of a sum)
+    assert float((matmul_nt(ones, b).double() - ones.double() @ b.double().t()).abs().max()) <= 2e-6 * R ** 0.5 * 4
+
+
+def test_equal_linear_first_and_second_order_vs_oracle():
+    """EqualLinear (fused_lrelu head) on the hand-written GEMM: value, gradients and the R1-style double backward
+    (gradient of |d out / d x|^2 w.r.t. the weights) against the oracle's torch formulation."""
+    from ideas_b200.stylegan2.model import EqualLinear
+    torch.manual_seed(3)
+    lin = EqualLinear(96, 40, activation="fused_lrelu", lr_mul=0.5)
+    lin.bias.data.normal_()
+    x = torch.randn(7, 96)
+    w, b = lin.weight.detach().clone().requires_grad_(True), lin.bias.detach().clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    yr = O.equal_linear(xr, w, b, lr_mul=0.5, activation="fused_lrelu")
+    (gr,) = torch.autograd.grad(yr.sum(), xr, create_graph=True)
+    pen_r = gr.pow(2).sum()
+    want = torch.autograd.grad(pen_r + yr.pow(2).sum(), [w, b, xr])
+    lin = lin.cuda()
+    xc = x.cuda().requires_grad_(True)
+    yc = lin(xc)
+    (gc,) = torch.autograd.grad(yc.sum(), xc, create_graph=True)
+    got = torch.autograd.grad(gc.pow(2).sum() + yc.pow(2).sum(), [lin.weight, lin.bias, xc])
+    assert rel(yc, yr) <= 2e-6
+    for a, c, name in zip(got, want, ("dW", "db", "dx")):
+        assert rel(a, c) <= 2e-5, (name, rel(a, c))

@@ -265,3 +265,112 @@ def test_tf32_error_level_vs_fp64():
     print(f"max rel err vs fp64: FFMA fp32 {e_simt:.2e}; tcgen05 tf32 rounded by TMA {e_round:.2e} (bias {b_round:.1e}); "
           f"truncated {e_trunc:.2e} (bias {b_trunc:.1e})")
     assert e_simt <= 1e-5 and e_round <= 5e-4 and abs(b_round) <= 1e-4 and e_trunc <= 1.5e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# pixel-major halo kernel (conv_umma_pmh_kernel): forced on ("pmh" = 2) for every eligible launch and compared with
+# the FFMA kernel.  Shapes: the 32 / 64-channel layers it exists for (E / Dco / Dreal first blocks), output tiles of
+# 32, 64 and 128 channels, ragged tiles in x and y, 2x2 filters, several k-tiles, the stride-2 data gradient with
+# its strided destination, and the residual-merging epilogue (ideas_conv2d_forward_res).
+class _opt:
+    def __init__(self, name, mode, default=1):
+        self.name, self.mode, self.default = name, mode, default
+
+    def __enter__(self):
+        _lib().call("ideas_set_option", self.name, self.mode)
+
+    def __exit__(self, *a):
+        _lib().call("ideas_set_option", self.name, self.default)
+
+
+PMH_FWD_CASES = [
+    # N, C, K, H, W, k, pad
+    (2, 32, 64, 16, 16, 3, 1),
+    (1, 32, 64, 258, 258, 3, 0),         # E first block (reflection-padded input)
+    (3, 32, 64, 64, 64, 3, 1),           # Dco first block
+    (1, 64, 128, 256, 256, 3, 1),        # Dreal first block (OCT = 128)
+    (2, 64, 64, 37, 29, 3, 1),           # ragged both ways
+    (2, 128, 64, 66, 66, 3, 0),          # data-gradient shape of a 64 -> 128 conv
+    (2, 96, 32, 20, 12, 3, 1),           # OCT = 32
+    (2, 64, 160, 9, 50, 3, 1),           # K = 160 = 5 x 32
+    (2, 64, 192, 40, 24, 3, 1),          # K = 192 = 3 x 64
+    (4, 384, 384, 14, 14, 3, 1),         # several channel steps, 3 k-tiles of 128
+    (4, 768, 384, 17, 17, 2, 0),         # 2x2 valid conv
+    (1, 128, 128, 130, 258, 3, 0),       # wide rows (bwp up to 256)
+    (5, 64, 64, 5, 7, 3, 1),             # tiny maps
+]
+
+
+@pytest.mark.parametrize("case", PMH_FWD_CASES)
+def test_pmh_forward_matches_simt(case):
+    L = _lib()
+    N, C, K, H, W, k, pad = case
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g)
+    wp = torch.randn(k * k, K, C, device="cuda", generator=g) / (C * k * k) ** 0.5
+    d = torch.rand(N, K, device="cuda", generator=g) + 0.5
+    b = torch.randn(K, device="cuda", generator=g)
+    ref = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_SIMT, d, b, 1)
+    n0 = L.launch_count()
+    with _opt(b"pmh", 2):
+        got = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA, d, b, 1)
+        plain = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA)
+    torch.cuda.synchronize()
+    assert L.launch_count() - n0 == 2
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+    assert rel(plain, conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_SIMT)) <= 1e-3
+    with _opt(b"pmh", 0), _opt(b"halo", 0):
+        old = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA, d, b, 1)
+    assert rel(got, old) <= 2e-5, rel(got, old)          # same tf32 products, different summation order only
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES + [(2, 128, 128, 64, 64, 3, 1, 1), (1, 64, 32, 40, 24, 3, 1, 1),
+                                                (2, 64, 128, 130, 130, 3, 1, 0)])
+def test_pmh_dgrad_matches_simt(case):
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(8)
+    dy = torch.randn(N, OH, OW, K, device="cuda", generator=g)
+    wpt = torch.randn(k * k, C, K, device="cuda", generator=g) / (K * k * k) ** 0.5
+    s = torch.rand(N, C, device="cuda", generator=g) + 0.5
+    ref = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_SIMT, s)
+    with _opt(b"pmh", 2):
+        got = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_AUTO, s)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 33, 21, 3, 1, 1, 2), (2, 128, 128, 32, 32, 3, 1, 1, 2),
+                                  (1, 512, 512, 32, 32, 3, 1, 1, 1), (2, 64, 128, 65, 65, 3, 2, 0, 1),
+                                  (2, 24, 40, 9, 9, 3, 1, 1, 1)])
+def test_conv_forward_residual_epilogue(case):
+    """y = (lrelu(d * conv(x) + b) * gain + residual) * res_scale through ideas_conv2d_forward_res on the pixel-major
+    halo kernel (pmh forced), the pixel-major kernel and the FFMA kernel, against the unfused composition."""
+    L = _lib()
+    N, C, K, H, W, k, stride, pad, pmh = case
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g)
+    wp = torch.randn(k * k, K, C, device="cuda", generator=g) / (C * k * k) ** 0.5
+    d = torch.rand(N, K, device="cuda", generator=g) + 0.5
+    b = torch.randn(K, device="cuda", generator=g)
+    res = torch.randn(N, OH, OW, K, device="cuda", generator=g)
+    rs = 2 ** -0.5
+    want = (conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_SIMT, d, b, 1) + res) * rs
+
+    def run(impl):
+        y = torch.full((N, OH, OW, K), float("nan"), device="cuda")
+        L.call("ideas_conv2d_forward_res", _p(y), _p(x), _p(wp), _p(None), _p(d), _p(b), _p(res), rs, N, H, W, C, K, k, k,
+               stride, pad, 1, 0.2, 2 ** 0.5, impl, _stream(x))
+        return y
+
+    assert rel(run(L.IMPL_SIMT), want) <= 1e-6
+    if C % 32 == 0 and K % 32 == 0:
+        with _opt(b"pmh", pmh):
+            got = run(L.IMPL_UMMA)
+        torch.cuda.synchronize()
+        assert not torch.isnan(got).any()
+        assert rel(got, want) <= 1e-3, rel(got, want)

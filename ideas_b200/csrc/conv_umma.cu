@@ -718,6 +718,8 @@ struct alignas(64) PmhParams {
   TapH taps[kMaxTaps];
 };
 
+constexpr uint32_t kPmhStageBytes = kPmhEpiWarps * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
+
 __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __grid_constant__ PmhParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t wfull[kPmhMaxWStages];
@@ -837,6 +839,11 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
   } else {
     // ===== epilogue: warps 3..10; TMEM lane quarter = warp % 4 (lane = slab position inside the sub-tile); the two
     // warps of a quarter take alternate (sub-tile, 32-channel chunk) units =====
+    // A unit is a 32-position x 32-channel block.  tcgen05.ld hands every thread one position's 32 channels; stored
+    // like that, a warp instruction would touch 32 separate 16-byte pieces 4*OC bytes apart.  The block therefore
+    // goes through a private 4 KB shared-memory tile (16-byte chunks XOR-swizzled by the row, conflict-free both
+    // ways) and comes back transposed: lane l owns chunk l%8 of positions l/8 + 4j, so one instruction writes four
+    // complete 128-byte lines -- and the per-channel operands (demodulation, bias) are loaded once per unit.
     const int quarter = warp & 3;
     const int half = (warp - 3) >> 2;
     const int cpt = p.oct >> 5;
@@ -844,6 +851,9 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
     const bool lrelu_on = p.act == IDEAS_ACT_LRELU;
     const float alpha = p.alpha, gain = lrelu_on ? p.gain : 1.f;
     const float rs = p.res_scale;
+    const uint32_t stage = xring + p.x_stages * p.x_slot_bytes + (uint32_t)(warp - 3) * 4096u;
+    const int cj = lane & 7;          // 16-byte chunk (4 channels) this lane stores
+    const int pr = lane >> 3;         // position within each group of four
     int it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       IDEAS_PMH_DECODE(item)
@@ -858,35 +868,41 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
       for (int u = half; u < units; u += 2) {
         const int sub = u / cpt;
         const int ch = u - sub * cpt;
-        const int m = sub * 128 + quarter * 32 + lane;
-        const int y = m / p.bwp;
-        const int x = m - y * p.bwp;
         float v[32];
         ptx::tmem_ld_32x32(acc + (uint32_t)(sub * p.oct + ch * 32), v);
-        if (x < xlim && y < ylim) {
-          const int64_t off = base + ((int64_t)y * p.o_s * p.OW + (int64_t)x * p.o_s) * p.OC + ch * 32;
-          float* dp = p.dst + off;
-          const float* rp = p.residual ? p.residual + off : nullptr;
+        __syncwarp();                                   // the previous unit's reads of the tile are done
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            if (osn) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(osn + ch * 32 + i));
-              r.x *= s4.x; r.y *= s4.y; r.z *= s4.z; r.w *= s4.w;
-            }
-            if (p.bias) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + i));
-              r.x += b4.x; r.y += b4.y; r.z += b4.z; r.w += b4.w;
-            }
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = stage + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+        }
+        __syncwarp();
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (osn) s4 = __ldg(reinterpret_cast<const float4*>(osn + ch * 32 + cj * 4));
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + cj * 4));
+        const int m0 = sub * 128 + quarter * 32 + pr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int row = 4 * j + pr;
+          const int m = m0 + 4 * j;
+          const int y = m / p.bwp;
+          const int x = m - y * p.bwp;
+          float4 r;
+          const uint32_t a = stage + (uint32_t)row * 128u + (uint32_t)((cj ^ (row & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+          if (x < xlim && y < ylim) {
+            const int64_t off = base + ((int64_t)y * p.o_s * p.OW + (int64_t)x * p.o_s) * p.OC + ch * 32 + cj * 4;
+            r.x = fmaf(r.x, s4.x, b4.x); r.y = fmaf(r.y, s4.y, b4.y); r.z = fmaf(r.z, s4.z, b4.z); r.w = fmaf(r.w, s4.w, b4.w);
             if (lrelu_on) {
-              r.x = lrelu(r.x, alpha) * gain; r.y = lrelu(r.y, alpha) * gain;
-              r.z = lrelu(r.z, alpha) * gain; r.w = lrelu(r.w, alpha) * gain;
+              r.x = lrelu(r.x, alpha); r.y = lrelu(r.y, alpha); r.z = lrelu(r.z, alpha); r.w = lrelu(r.w, alpha);
             }
-            if (rp) {
-              const float4 q = ld_stream4(rp + i);
+            r.x *= gain; r.y *= gain; r.z *= gain; r.w *= gain;
+            if (p.residual) {
+              const float4 q = ld_stream4(p.residual + off);
               r.x = (r.x + q.x) * rs; r.y = (r.y + q.y) * rs; r.z = (r.z + q.z) * rs; r.w = (r.w + q.w) * rs;
             }
-            *reinterpret_cast<float4*>(dp + i) = r;
+            *reinterpret_cast<float4*>(p.dst + off) = r;
           }
         }
       }
@@ -931,7 +947,7 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile
       const int nsub = ceil_div(bh * bwp, 128);
       if (nsub > max_sub) break;
       const uint32_t slot = (uint32_t)((nsub * 128 + hy * bwp + hx) * 128 + 1023) & ~1023u;
-      if (2 * slot + 4 * w_bytes > kPmhSmemBudget) break;
+      if (2 * slot + 4 * w_bytes + kPmhStageBytes > kPmhSmemBudget) break;
       const int tx = ceil_div(QW, bw), ty = ceil_div(QH, bh);
       const double mma = (double)ntaps * nsub * 4 * (oct / 2.0);
       const double l2 = ((double)ntaps * w_bytes + (double)(bh + hy) * bwp * 128) / 48.0;
@@ -939,7 +955,7 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile
       if (cyc < best.cycles) {
         best.bw = bw; best.bwp = bwp; best.bh = bh; best.nsub = nsub; best.tiles_x = tx; best.tiles_y = ty;
         best.slot_bytes = slot; best.cycles = cyc;
-        const int ws = (int)((kPmhSmemBudget - 2 * slot) / w_bytes);
+        const int ws = (int)((kPmhSmemBudget - kPmhStageBytes - 2 * slot) / w_bytes);
         best.w_stages = ws > kPmhMaxWStages ? kPmhMaxWStages : ws;
       }
     }
@@ -1014,7 +1030,7 @@ int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float
     int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
     if (rc) return rc;
   }
-  const uint32_t smem = p.w_stages * p.w_bytes + p.x_stages * p.x_slot_bytes + 1024;
+  const uint32_t smem = p.w_stages * p.w_bytes + p.x_stages * p.x_slot_bytes + kPmhStageBytes + 1024;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

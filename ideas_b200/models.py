@@ -249,7 +249,7 @@ class Generator(nn.Module):
             return (torch.cat([m.effective_weight() for m in lins], 0),
                     torch.cat([m.bias * m.lr_mul for m in lins], 0))
 
-        w_all, b_all = cached(lins[0].weight, ("G.modulations", tuple(m.weight._version for m in lins)), build)
+        w_all, b_all = cached(lins[0].weight, "G.modulations", build)
         s_all = matmul_nt(texture, w_all) + b_all
         parts = torch.split(s_all, [m.weight.shape[0] for m in lins], dim=1)
         return [(parts[2 * i], parts[2 * i + 1]) for i in range(len(self.layers))]

@@ -50,12 +50,19 @@ class _StepCache:
     """Packed weights (and the other tensors derived from a parameter alone) are functions of the parameter, which
     changes once per optimiser step -- yet a training iteration runs E twice, G and Dreal three to six times.  Inside
     ``step_scope()`` such tensors are built once per (parameter, version, grad mode) and shared by every use: one
-    PackWeight node per weight and phase, whose gradient autograd accumulates before ONE unpack.  The key carries
-    ``Tensor._version`` (bumped by every in-place optimiser update, also while a CUDA graph is being captured), and
-    the cache is dropped when the scope exits, so nothing derived from stale weights -- or living in a graph's
-    private memory pool -- can be seen outside the iteration that built it."""
+    PackWeight node per weight and phase, whose gradient autograd accumulates before ONE unpack.  Entries derived
+    from a parameter are keyed by the parameter's ``_version`` AND by an epoch that the owner of the scope advances
+    after every optimiser step (``invalidate_step_cache``; fused Adam updates parameters without touching their
+    version counters).  The cache is dropped when the scope exits, so nothing derived from stale weights -- or
+    living in a CUDA graph's private memory pool -- can be seen outside the iteration that built it."""
     depth = 0
+    epoch = 0
     store: dict = {}
+
+
+def invalidate_step_cache():
+    """Call after every optimiser step taken inside a step_scope (train_step.Trainer registers it as a step hook)."""
+    _StepCache.epoch += 1
 
 
 class step_scope:
@@ -72,11 +79,13 @@ class step_scope:
         return False
 
 
-def cached(key: torch.Tensor, tag, build):
-    """``build()`` once per (key tensor, version, autograd mode, tag) inside a step_scope; plain call outside."""
+def cached(key: torch.Tensor, tag, build, immutable: bool = False):
+    """``build()`` once per (key tensor, version, epoch, autograd mode, tag) inside a step_scope; plain call outside.
+    ``immutable``: the key is a temporary that nothing updates in place (a packed copy), so the epoch is ignored."""
     if _StepCache.depth == 0:
         return build()
-    k = (id(key), key._version, bool(key.requires_grad and torch.is_grad_enabled()), tag)
+    k = (id(key), key._version, -1 if immutable else _StepCache.epoch,
+         bool(key.requires_grad and torch.is_grad_enabled()), tag)
     hit = _StepCache.store.get(k)
     if hit is None:
         hit = (key, build())                 # holding ``key`` keeps id() unique while the entry lives
@@ -131,7 +140,7 @@ def _dgrad(dy, wp, g: Geom, in_scale=None, out_scale=None, impl=None):
         _lib.call("ideas_repack_dgrad", ptr(t), ptr(wp), g.K, g.C, g.kh * g.kw, stream_ptr(dy))
         return t
 
-    wpt = cached(wp, "dgrad", repack)
+    wpt = cached(wp, "dgrad", repack, immutable=True)
     dx = empty_nhwc(g.N, g.C, g.H, g.W, dy)
     _lib.call("ideas_conv2d_dgrad", ptr(dx), ptr(dy), ptr(wpt), ptr(in_scale), ptr(out_scale), ptr(None),
               g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, g.OH, g.OW, _lib.ACT_NONE, 0.2, 1.0,

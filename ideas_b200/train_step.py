@@ -123,9 +123,12 @@ class Trainer:
         r = args.d_reg_every / (args.d_reg_every + 1)
         self.d_optim = optim.Adam(P("Dreal", "Dco", "Ddist"), lr=args.lr * r, betas=(0.0 ** r, 0.99 ** r), **kw)
         self.reducers = {}
+        from .stylegan2.op.conv import invalidate_step_cache
         for name, opt in (("g", self.g_optim), ("ex", self.ex_optim), ("d", self.d_optim)):
             red = FlatGradAllReduce([p for grp in opt.param_groups for p in grp["params"]])
             opt.register_step_pre_hook(red)
+            # packed weights cached for the running iteration are stale once the optimiser has stepped
+            opt.register_step_post_hook(lambda *_: invalidate_step_cache())
             self.reducers[name] = red
         self.accum = 0.5 ** (32 / (10 * 1000))                          # train.py:30
 

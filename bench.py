@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--case", default=None, help="run ONE roofline kernel alone (for ncu); see CASES in bench.py")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--no-batch-g", action="store_true", help="A/B: three Generator calls per phase instead of one batched call")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--prune-dead-backward", action="store_true",
                     help="NOT the default measurement: restrict the loop's second backward (train.py:214-216) to Ex's parameters")
@@ -414,7 +415,7 @@ def run_ours(args):
     B, S = args.batch, args.image_size
     targs = default_args(batch_size=B, image_size=S)
     tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
-                 prune_dead_backward=args.prune_dead_backward)
+                 prune_dead_backward=args.prune_dead_backward, batch_generator=not args.no_batch_g)
     tr.broadcast_parameters(0)
     import random
     torch.manual_seed(1000 + rank)                   # per-rank data / Z / T2 / crops

@@ -140,6 +140,10 @@ def lib() -> ctypes.CDLL:
         L.ideas_launch_count.argtypes = []
         L.ideas_launch_count.restype = ctypes.c_ulonglong
         _lib = L
+        # kernel-selection options for A/B measurements, e.g. IDEAS_OPTS=pmh=0,halo=2 (see ideas_set_option)
+        for kv in filter(None, os.environ.get("IDEAS_OPTS", "").split(",")):
+            name, val = kv.split("=")
+            check(L.ideas_set_option(name.encode(), int(val)), "ideas_set_option")
     return _lib
 
 

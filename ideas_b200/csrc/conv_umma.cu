@@ -694,6 +694,8 @@ constexpr int kPmhEpiWarps = 8;
 constexpr uint32_t kPmhSmemBudget = 224 * 1024;
 
 std::atomic<int> g_pmh_mode{1};               // 0 = never, 1 = heuristic, 2 = whenever eligible
+std::atomic<int> g_pmh_xstages{2};            // slab ring depth (2 or 3)
+std::atomic<int> g_pmh_minbw{0};              // tile search: smallest tile width considered (0 = no bound)
 
 struct alignas(64) PmhParams {
   CUtensorMap src;
@@ -921,7 +923,7 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
 }
 
 struct PmhTile {
-  int bw, bwp, bh, nsub, tiles_x, tiles_y, w_stages;
+  int bw, bwp, bh, nsub, tiles_x, tiles_y, w_stages, x_stages;
   uint32_t slot_bytes;
   double cycles;
 };
@@ -931,7 +933,9 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile
   struct Key { int a, b, c, d, e, f; bool operator<(const Key& o) const { return memcmp(this, &o, sizeof(Key)) < 0; } };
   static std::mutex mu;
   static std::map<Key, PmhTile> cache;
-  const Key key{QW, QH, hx, hy, ntaps, oct};
+  const int xst = g_pmh_xstages.load() == 3 ? 3 : 2;
+  const int minbw = g_pmh_minbw.load();
+  const Key key{QW, QH, hx * 16 + hy, ntaps, oct, xst * 1024 + minbw};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -941,13 +945,15 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile
   best.bw = 0; best.cycles = 1e300;
   const uint32_t w_bytes = (uint32_t)oct * 128u;
   const int max_sub = 256 / oct;
-  for (int bw = (QW < 4 ? QW : 4); bw <= QW && bw + hx <= 256; ++bw) {
+  int bw0 = QW < 4 ? QW : 4;
+  if (minbw > bw0) bw0 = minbw < QW ? minbw : QW;
+  for (int bw = bw0; bw <= QW && bw + hx <= 256; ++bw) {
     const int bwp = bw + hx;
     for (int bh = 1; bh <= QH && bh + hy <= 256; ++bh) {
       const int nsub = ceil_div(bh * bwp, 128);
       if (nsub > max_sub) break;
       const uint32_t slot = (uint32_t)((nsub * 128 + hy * bwp + hx) * 128 + 1023) & ~1023u;
-      if (2 * slot + 4 * w_bytes + kPmhStageBytes > kPmhSmemBudget) break;
+      if (xst * slot + 4 * w_bytes + kPmhStageBytes > kPmhSmemBudget) break;
       const int tx = ceil_div(QW, bw), ty = ceil_div(QH, bh);
       const double mma = (double)ntaps * nsub * 4 * (oct / 2.0);
       const double l2 = ((double)ntaps * w_bytes + (double)(bh + hy) * bwp * 128) / 48.0;
@@ -955,8 +961,9 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile
       if (cyc < best.cycles) {
         best.bw = bw; best.bwp = bwp; best.bh = bh; best.nsub = nsub; best.tiles_x = tx; best.tiles_y = ty;
         best.slot_bytes = slot; best.cycles = cyc;
-        const int ws = (int)((kPmhSmemBudget - kPmhStageBytes - 2 * slot) / w_bytes);
+        const int ws = (int)((kPmhSmemBudget - kPmhStageBytes - xst * slot) / w_bytes);
         best.w_stages = ws > kPmhMaxWStages ? kPmhMaxWStages : ws;
+        best.x_stages = xst;
       }
     }
   }
@@ -1006,7 +1013,7 @@ int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float
   if (items > (1ll << 30)) return IDEAS_ERR_UNSUPPORTED;
   p.items = (int)items;
   p.ntaps = g.ntaps; p.csteps = g.IC / kBlockK;
-  p.x_stages = 2;
+  p.x_stages = tile.x_stages;
   p.w_stages = tile.w_stages;
   p.x_slot_bytes = tile.slot_bytes;
   p.x_tx_bytes = (uint32_t)(p.box_rows * p.bwp * 128);
@@ -1494,6 +1501,14 @@ extern "C" int ideas_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "pmh")) {
     ideas::g_pmh_mode.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pmh_xstages")) {
+    ideas::g_pmh_xstages.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pmh_minbw")) {
+    ideas::g_pmh_minbw.store(value);
     return IDEAS_OK;
   }
   ideas::set_error("ideas_set_option: unknown option '%s'", name ? name : "(null)");

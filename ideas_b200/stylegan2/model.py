@@ -28,6 +28,11 @@ from .op.linear import matmul_nt
 from .._tensor import nhwc
 
 
+import os as _os
+
+_AB_CUBLAS_LINEAR = _os.environ.get("IDEAS_AB_CUBLAS_LINEAR", "0") == "1"
+
+
 class PixelNorm(nn.Module):
     def forward(self, input):
         return input * torch.rsqrt(torch.mean(input ** 2, dim=1, keepdim=True) + 1e-8)
@@ -135,6 +140,11 @@ class EqualLinear(nn.Module):
 
     def forward(self, input):
         lead = input.shape[:-1]
+        if _AB_CUBLAS_LINEAR:           # measurement-only A/B switch (IDEAS_AB_CUBLAS_LINEAR=1): library GEMM instead of ours
+            out = F.linear(input, self.effective_weight())
+            if self.activation:
+                return fused_leaky_relu(out, self.bias * self.lr_mul)
+            return out if self.bias is None else out + self.bias * self.lr_mul
         out = matmul_nt(input.reshape(-1, input.shape[-1]), self.effective_weight())   # hand-written fp32 GEMM
         if self.activation:
             return fused_leaky_relu(out, self.bias * self.lr_mul).reshape(*lead, -1)

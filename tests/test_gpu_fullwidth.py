@@ -42,7 +42,7 @@ def test_cfg3_layer_full_width_vs_oracle():
         T.record(f"cfg3_B2.{name}.rel_l2", T.rel_l2(a, b))
         if a.numel() >= 10000:
             T.record(f"cfg3_B2.{name}.q95", T.rel_q(a, b))
-        T.assert_grad_through_act(a, b, "tf32", name)
+        T.assert_grad_through_act(a, b, "tf32", name, reduced="modulation" in name or name == "dstyle")
 
 
 def test_wgrad_million_pixel_reduction_vs_fp64():
@@ -68,9 +68,9 @@ def test_wgrad_million_pixel_reduction_vs_fp64():
     got = dwp[:, ks, :].double()
     scale = ref.abs().max()
     err = float((got - ref).abs().max() / scale)
-    T.record("wgrad_K1M.max_abs_over_max", err, 2e-3)
+    T.record("wgrad_K1M.max_abs_over_max", err, 6e-4)
     rms = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
-    T.record("wgrad_K1M.rel_rms", rms, 1e-3)
+    T.record("wgrad_K1M.rel_rms", rms, 6e-4)
     # tf32 rounding errors of the 1 M products are independent: the sum's error grows like sqrt(K) * 2^-11 * |x||dy|,
     # the same scaling as the sum itself for random data, so the relative error stays at the single-product level
-    assert err <= 2e-3 and rms <= 1e-3, (err, rms)
+    assert err <= 6e-4 and rms <= 6e-4, (err, rms)          # measured 3.0e-4 / 3.1e-4

@@ -92,7 +92,7 @@ def test_small_nets_match_reference(golden_dir, conv_mode):
 def test_cfg1_pipeline_and_bit_exact_extraction(golden_dir, conv_mode):
     """BASELINE.json configs[0]: 64x64 E -> Gstru -> G -> E -> Ex on 2 images, then the bit path."""
     from ideas_b200.models import init_model
-    TOL = TOLS.NET[conv_mode] * (2 if conv_mode == "tf32" else 1)      # E -> G -> E: three networks deep
+    TOL = TOLS.NET_CFG1[conv_mode]                                     # SURVEY §8(d) cfg 1: 1e-3
     from ideas_b200 import utils as U
     g = torch.load(os.path.join(golden_dir, "cfg1.pt"))
     torch.manual_seed(0)
@@ -190,6 +190,7 @@ def test_train_step_matches_oracle(conv_mode, multi_stream):
         for k, v in lo.items():
             got = float(lg[k])
             tol = 2e-3 if conv_mode == "fp32" else 5e-3
+            TOLS.record(f"step_c4.{conv_mode}.it{it}.loss.{k}", abs(got - float(v)) / max(1.0, abs(float(v))), tol)
             assert abs(got - float(v)) <= tol * max(1.0, abs(float(v))), (it, k, got, float(v))
     worst = 0.0
     for k in ("E", "G", "Gstru", "Ex", "Dreal", "Dco", "Ddist"):
@@ -201,6 +202,7 @@ def test_train_step_matches_oracle(conv_mode, multi_stream):
             worst = max(worst, err)
     # Adam with beta1 = 0 moves every weight by ~lr = 2e-3 per step whatever the gradient's size, and
     # flips sign where a gradient is ~0 (worst case 2 steps x 2 lr); the bulk must agree far better
+    TOLS.record(f"step_c4.{conv_mode}.worst_param_delta", worst, 1.3e-2)
     assert worst <= 1.3e-2, worst
     frac_bad = 0
     total = 0
@@ -212,6 +214,7 @@ def test_train_step_matches_oracle(conv_mode, multi_stream):
             diff = (mine[n].cpu() - want.detach()).abs()
             frac_bad += int((diff > 4e-4).sum())
             total += diff.numel()
+    TOLS.record(f"step_c4.{conv_mode}.frac_params_off_by_4e-4", frac_bad / total)
     assert frac_bad / total < (0.02 if conv_mode == "fp32" else 0.08), frac_bad / total
 
 
@@ -234,8 +237,8 @@ def test_train_step_channel32_all_nets_on_tcgen05():
     lg = tr.step(X.cuda(), 1, draws)
     for k, v in lo.items():
         got = float(lg[k])
-        e = TOLS.record(f"step_c32.loss.{k}", abs(got - float(v)) / max(1.0, abs(float(v))), 5e-3)
-        assert e <= 5e-3, (k, got, float(v))
+        e = TOLS.record(f"step_c32.loss.{k}", abs(got - float(v)) / max(1.0, abs(float(v))), 1e-3)
+        assert e <= 1e-3, (k, got, float(v))                           # measured <= 3.8e-4
     # Adam with beta1 = 0 moves every weight by +-lr*(1 - tiny): compare the DIRECTION of the update, which is the
     # sign of the gradient, over the elements whose oracle gradient is not ~0 (|update| at full size)
     lr = args.lr
@@ -273,8 +276,8 @@ def test_multi_stream_eager_step_is_race_free():
         del tr
     for other in runs[1:]:
         for k, v in runs[0].items():
-            e = TOLS.record(f"multistream_eager.{k}", abs(other[k] - v) / max(1.0, abs(v)), 1e-4)
-            assert e <= 1e-4, (k, v, other[k])
+            e = TOLS.record(f"multistream_eager.{k}", abs(other[k] - v) / max(1.0, abs(v)), 5e-6)
+            assert e <= 5e-6, (k, v, other[k])                          # measured <= 5.4e-7 (atomics order)
 
 
 def test_graph_replay_multi_stream_matches_single_stream():

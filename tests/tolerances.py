@@ -15,9 +15,15 @@ Whole networks (16+ stacked ops) get a proportionally wider output tolerance.
 """
 import torch
 
-OUT = {"fp32": 3e-5, "tf32": 1e-3}          # one op, forward
-GRAD = {"fp32": 1e-4, "tf32": 3e-3}         # one op, backward (no activation mask in between)
-NET = {"fp32": 1e-4, "tf32": 5e-3}          # whole network forward
+# Set from the errors measured on a B200 (gpurun_out/parity_errors.jsonl, summarised in DESIGN.md §4): each bound is
+# about twice the worst value observed, and never looser than the north-star 1e-3 for a single op.
+OUT = {"fp32": 3e-5, "tf32": 7e-4}          # one op, forward                       (measured <= 3.3e-4)
+GRAD = {"fp32": 1e-4, "tf32": 1e-3}         # one op, backward, no activation mask  (measured <= 3.3e-4)
+NET = {"fp32": 1e-4, "tf32": 2.5e-3}        # whole network forward at reduced size (measured <= 1.3e-3)
+NET_CFG1 = {"fp32": 1e-4, "tf32": 1e-3}     # BASELINE cfg 1, SURVEY §8(d): <= 1e-3 (measured <= 9.0e-4, E -> G -> E -> Ex)
+NET_256 = {"fp32": 2e-4, "tf32": 7e-3}      # G at full depth and width on 256x256  (measured 3.5e-3)
+GRAD_ACT_Q95 = 3e-3                         # gradients through a leaky-ReLU mask: 95th percentile (measured <= 1.7e-3)
+GRAD_ACT_L2 = 3e-2                          #   and relative L2 (measured <= 1.5e-2; mask flips, see above)
 
 
 def _auto(kind, v):
@@ -47,16 +53,17 @@ def rel_q(a, b, q=0.95):
     return _auto("q95", float(torch.quantile(d, q) / b.abs().max().clamp_min(1e-9)))
 
 
-def assert_grad_through_act(a, b, mode, what=""):
-    """gradient comparison that tolerates leaky-ReLU mask flips in tf32 mode (see module docstring)."""
+def assert_grad_through_act(a, b, mode, what="", reduced=False):
+    """gradient comparison that tolerates leaky-ReLU mask flips in tf32 mode (see module docstring).
+    ``reduced``: the tensor is a reduction over all pixels (style, bias, modulation-weight gradients): every flip
+    lands in every element, so only the relative L2 error is meaningful."""
     if mode == "fp32":
         assert rel(a, b) <= GRAD["fp32"], (what, rel(a, b))
-    elif a.numel() < 10000:
-        # small reductions over all pixels (style, bias, per-sample scale gradients): every flip lands in them
-        assert rel_l2(a, b) <= 5e-2, (what, "l2", rel_l2(a, b))
+    elif a.numel() < 10000 or reduced:
+        assert rel_l2(a, b) <= GRAD_ACT_L2, (what, "l2", rel_l2(a, b))
     else:
-        assert rel_q(a, b) <= GRAD["tf32"], (what, "q95", rel_q(a, b))
-        assert rel_l2(a, b) <= 5e-2, (what, "l2", rel_l2(a, b))
+        assert rel_q(a, b) <= GRAD_ACT_Q95, (what, "q95", rel_q(a, b))
+        assert rel_l2(a, b) <= GRAD_ACT_L2, (what, "l2", rel_l2(a, b))
 
 
 def record(name, value, tol=None):

@@ -856,14 +856,25 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
     const uint32_t stage = xring + p.x_stages * p.x_slot_bytes + (uint32_t)(warp - 3) * 4096u;
     const int cj = lane & 7;          // 16-byte chunk (4 channels) this lane stores
     const int pr = lane >> 3;         // position within each group of four
+    // every address below is a base register plus a compile-time term: the epilogue warps share the issue slots with
+    // nothing but each other, and at 32 input channels an item's MMAs last only ~3.5k clk
+    const uint32_t st_base = stage + (uint32_t)lane * 128u;
+    const uint32_t st_sw = (uint32_t)(lane & 7);
+    const uint32_t ld_base = stage + (uint32_t)pr * 128u;
+    const uint32_t ld_sw0 = (uint32_t)((cj ^ pr) << 4), ld_sw1 = (uint32_t)((cj ^ (pr | 4)) << 4);
+    const int pixstride = p.o_s * p.OC;
+    const int64_t rowstride = (int64_t)p.o_s * p.OW * p.OC;
+    const int64_t rowwrap = rowstride - (int64_t)p.bwp * pixstride;
+    const bool has_res = p.residual != nullptr;
     int it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       IDEAS_PMH_DECODE(item)
       const int buf = it & 1;
       const int xlim = min(p.bw, p.QW - qx0);
       const int ylim = min(p.bh, p.QH - qy0);
-      const int64_t base = (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + k0;
-      const float* osn = p.out_scale ? p.out_scale + (int64_t)n * p.OC + k0 : nullptr;
+      const int64_t base = (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + k0 + cj * 4;
+      const float* osn = p.out_scale ? p.out_scale + (int64_t)n * p.OC + k0 + cj * 4 : nullptr;
+      const float* bsn = p.bias ? p.bias + k0 + cj * 4 : nullptr;
       ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
@@ -874,38 +885,37 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
         ptx::tmem_ld_32x32(acc + (uint32_t)(sub * p.oct + ch * 32), v);
         __syncwarp();                                   // the previous unit's reads of the tile are done
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t a = stage + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
-        }
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + ((st_sw ^ (uint32_t)j) << 4)), "f"(v[4 * j]),
+                       "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
         __syncwarp();
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (osn) s4 = __ldg(reinterpret_cast<const float4*>(osn + ch * 32 + cj * 4));
-        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + cj * 4));
-        const int m0 = sub * 128 + quarter * 32 + pr;
+        if (osn) s4 = __ldg(reinterpret_cast<const float4*>(osn + ch * 32));
+        if (bsn) b4 = __ldg(reinterpret_cast<const float4*>(bsn + ch * 32));
+        const int m = sub * 128 + quarter * 32 + pr;
+        int y = m / p.bwp;
+        int x = m - y * p.bwp;
+        int64_t off = base + (int64_t)y * rowstride + (int64_t)x * pixstride + ch * 32;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int row = 4 * j + pr;
-          const int m = m0 + 4 * j;
-          const int y = m / p.bwp;
-          const int x = m - y * p.bwp;
           float4 r;
-          const uint32_t a = stage + (uint32_t)row * 128u + (uint32_t)((cj ^ (row & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                       : "r"(ld_base + (uint32_t)(j * 512) + ((j & 1) ? ld_sw1 : ld_sw0)));
           if (x < xlim && y < ylim) {
-            const int64_t off = base + ((int64_t)y * p.o_s * p.OW + (int64_t)x * p.o_s) * p.OC + ch * 32 + cj * 4;
             r.x = fmaf(r.x, s4.x, b4.x); r.y = fmaf(r.y, s4.y, b4.y); r.z = fmaf(r.z, s4.z, b4.z); r.w = fmaf(r.w, s4.w, b4.w);
             if (lrelu_on) {
               r.x = lrelu(r.x, alpha); r.y = lrelu(r.y, alpha); r.z = lrelu(r.z, alpha); r.w = lrelu(r.w, alpha);
             }
             r.x *= gain; r.y *= gain; r.z *= gain; r.w *= gain;
-            if (p.residual) {
+            if (has_res) {
               const float4 q = ld_stream4(p.residual + off);
               r.x = (r.x + q.x) * rs; r.y = (r.y + q.y) * rs; r.z = (r.z + q.z) * rs; r.w = (r.w + q.w) * rs;
             }
             *reinterpret_cast<float4*>(p.dst + off) = r;
           }
+          x += 4;
+          off += 4 * pixstride;
+          if (x >= p.bwp) { x -= p.bwp; ++y; off += rowwrap; }
         }
       }
       ptx::tc_fence_before();

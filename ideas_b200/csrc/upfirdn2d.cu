@@ -30,6 +30,8 @@ struct UpfirdnParams {
   int up_x, up_y, down_x, down_y, pad_x0, pad_y0;
   int out_h, out_w;
   float alpha, gain;
+  const float* residual;   // out-shaped; merged as (result + residual) * res_scale (up2 fast path only)
+  float res_scale;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -523,8 +525,16 @@ __global__ void __launch_bounds__(128) blur4_up2_kernel(float* __restrict__ out,
   const int64_t orow = (int64_t)p.out_w * p.minor;
   if (!sep) {
     for (int oy = oy0; oy < oy1; ++oy)
-      for (int j = 0; j < NO && ox0 + j < p.out_w; ++j)
-        st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, upfirdn_direct4(x, kernel, p, m, oy, ox0 + j, c));
+      for (int j = 0; j < NO && ox0 + j < p.out_w; ++j) {
+        float4 v = upfirdn_direct4(x, kernel, p, m, oy, ox0 + j, c);
+        float* dp = o + (int64_t)oy * orow + (int64_t)j * p.minor;
+        if (p.residual) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + (dp - out)));
+          v.x = (v.x + q.x) * p.res_scale; v.y = (v.y + q.y) * p.res_scale;
+          v.z = (v.z + q.z) * p.res_scale; v.w = (v.w + q.w) * p.res_scale;
+        }
+        st_stream4(dp, v);
+      }
     return;
   }
   unsigned long long kx[4], ky[4];
@@ -578,6 +588,12 @@ __global__ void __launch_bounds__(128) blur4_up2_kernel(float* __restrict__ out,
               f2x2 d;
               d.lo = fma2(hcur[j].lo, k2, mul2(hprev[j].lo, k0));
               d.hi = fma2(hcur[j].hi, k2, mul2(hprev[j].hi, k0));
+              if (p.residual) {
+                const unsigned long long rs2 = pack2(p.res_scale, p.res_scale);
+                const f2x2 q = ldg_f2x2(p.residual + (op - out) + (int64_t)j * p.minor);
+                d.lo = mul2(fma2(q.lo, pack2(1.f, 1.f), d.lo), rs2);
+                d.hi = mul2(fma2(q.hi, pack2(1.f, 1.f), d.hi), rs2);
+              }
               st_f2x2(op + (int64_t)j * p.minor, d);
             }
           }
@@ -598,6 +614,14 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
                                int minor, int kernel_h, int kernel_w, int up_x, int up_y, int down_x, int down_y,
                                int pad_x0, int pad_x1, int pad_y0, int pad_y1, const float* bias, float alpha,
                                float gain, void* stream) {
+  return ideas_upfirdn2d_res(out, x, kernel, major, in_h, in_w, minor, kernel_h, kernel_w, up_x, up_y, down_x, down_y, pad_x0,
+                             pad_x1, pad_y0, pad_y1, bias, alpha, gain, nullptr, 1.f, stream);
+}
+
+extern "C" int ideas_upfirdn2d_res(float* out, const float* x, const float* kernel, int major, int in_h, int in_w,
+                                   int minor, int kernel_h, int kernel_w, int up_x, int up_y, int down_x, int down_y,
+                                   int pad_x0, int pad_x1, int pad_y0, int pad_y1, const float* bias, float alpha,
+                                   float gain, const float* residual, float res_scale, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   IDEAS_REQUIRE(major >= 0 && in_h >= 0 && in_w >= 0 && minor >= 1, "upfirdn2d: bad input shape");
   IDEAS_REQUIRE(kernel_h >= 1 && kernel_w >= 1, "upfirdn2d: empty FIR kernel");
@@ -609,6 +633,7 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
   p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kernel_h + down_y) / down_y;
   p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kernel_w + down_x) / down_x;
   p.alpha = alpha; p.gain = gain;
+  p.residual = residual; p.res_scale = res_scale;
   const bool empty = major == 0 || in_h == 0 || in_w == 0;
   IDEAS_REQUIRE(empty || ((in_h * up_y + pad_y0 + pad_y1 - kernel_h) >= 0 && (in_w * up_x + pad_x0 + pad_x1 - kernel_w) >= 0),
                 "upfirdn2d: padding/cropping leaves no output (in %dx%d, kernel %dx%d)", in_h, in_w, kernel_h, kernel_w);
@@ -617,6 +642,14 @@ extern "C" int ideas_upfirdn2d(float* out, const float* x, const float* kernel, 
   if (total == 0) return IDEAS_OK;
   IDEAS_REQUIRE(out && x && kernel, "upfirdn2d: null pointer");
 
+  if (residual) {      // only the fused up-sampling path merges a residual; callers fall back to a separate merge otherwise
+    const bool ok = up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1 && kernel_h <= 4 && kernel_w <= 4 && minor % 4 == 0 &&
+                    aligned16(out) && aligned16(x) && aligned16(residual) && !bias && major <= 65535;
+    if (!ok) {
+      set_error("upfirdn2d: a residual operand needs the up=2 fast path (<= 4x4 kernel, channels %% 4 == 0, no bias)");
+      return IDEAS_ERR_UNSUPPORTED;
+    }
+  }
   const bool fast = up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kernel_h <= 4 && kernel_w <= 4 &&
                     minor % 4 == 0 && aligned16(out) && aligned16(x) && (!bias || aligned16(bias)) && major <= 65535;
   if (fast) {

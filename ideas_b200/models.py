@@ -21,6 +21,7 @@ from torch import nn
 from .stylegan2.model import (Blur, EqualConv2d, EqualLinear, ScaledLeakyReLU,
                               StyledConv_without_noise as StyledConv)
 from .stylegan2.op import FusedLeakyReLU, upfirdn2d
+from .stylegan2.op.upfirdn2d import residual_ok
 from .stylegan2.op import conv as _ops
 from .stylegan2.op.conv import cached, packed_weight
 from .stylegan2.op.linear import matmul_nt
@@ -117,13 +118,17 @@ class ConvLayer(nn.Sequential):
         super().__init__(*stages)
         self.padding = conv_pad
 
-    def forward(self, input, start=0):
-        """``start``: index of the first child to run (ResBlock fuses conv1's tail with conv2's leading Blur)."""
+    def forward(self, input, start=0, residual=None, res_scale=1.0):
+        """``start``: index of the first child to run (ResBlock fuses conv1's tail with conv2's leading Blur).
+        ``residual``: the layer returns (layer(input) + residual) * res_scale.  When the layer ends in an
+        activation-free convolution or in the blur of an up-sampling skip -- every skip path of the residual blocks
+        does -- the merge happens in that kernel's epilogue; otherwise it is one add_scale pass."""
         mods = list(self)
         i, out = start, input
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
+            last2, last1 = i + 2 >= len(mods), i + 1 >= len(mods)
             if isinstance(m, EqualConv2d) and isinstance(nxt, FusedLeakyReLU):
                 out = m(out, activation=nxt)          # one kernel: conv + bias + leaky ReLU
                 i += 2
@@ -131,18 +136,32 @@ class ConvLayer(nn.Sequential):
                   and nxt.stride == 2 and nxt.padding == 0):
                 # Blur -> 1x1 stride-2 conv (down-sampling skip): the conv reads every other blurred pixel, so
                 # blur and decimate in one pass (upfirdn2d down=2) and run the 1x1 conv at the low resolution
-                out = nxt(upfirdn2d(out, m.kernel, down=2, pad=m.pad), stride=1)
+                low = upfirdn2d(out, m.kernel, down=2, pad=m.pad)
+                if residual is not None and last2:
+                    out, residual = nxt(low, stride=1, residual=residual, res_scale=res_scale), None
+                else:
+                    out = nxt(low, stride=1)
                 i += 2
             elif (isinstance(m, EqualConvTranspose2d) and isinstance(nxt, Blur) and m.weight.shape[2] == 1
                   and m.stride == 2 and m.padding == 0 and m.bias is None):
                 # 1x1 stride-2 transposed conv -> Blur (up-sampling skip): a bias-free 1x1 conv commutes with zero
                 # insertion, so convolve at the low resolution and let upfirdn2d(up=2) interleave the zeros on the
                 # fly (its trailing zero replaces one unit of right padding)
-                out = upfirdn2d(m(out, stride=1), nxt.kernel, up=2, pad=(nxt.pad[0], nxt.pad[1] - 1))
+                low = m(out, stride=1)
+                pad = (nxt.pad[0], nxt.pad[1] - 1)
+                if residual is not None and last2 and residual_ok(low, nxt.kernel, (2, 2), (1, 1)):
+                    out, residual = upfirdn2d(low, nxt.kernel, up=2, pad=pad, residual=residual, res_scale=res_scale), None
+                else:
+                    out = upfirdn2d(low, nxt.kernel, up=2, pad=pad)
                 i += 2
+            elif isinstance(m, EqualConv2d) and residual is not None and last1:
+                out, residual = m(out, residual=residual, res_scale=res_scale), None
+                i += 1
             else:
                 out = m(out)
                 i += 1
+        if residual is not None:
+            out = add_scale(out, residual, res_scale)
         return out
 
 
@@ -160,8 +179,9 @@ class StyledResBlock(nn.Module):
         """``modulation``: optional (s1, s2), the outputs of conv1 / conv2's modulation linears."""
         m1, m2 = modulation if modulation is not None else (None, None)
         out = self.conv2(self.conv1(input, style, noise, modulation=m1), style, noise, modulation=m2)
-        skip = input if self.skip is None else self.skip(input)
-        return add_scale(out, skip, _INV_SQRT2)
+        if self.skip is None:
+            return add_scale(out, input, _INV_SQRT2)
+        return self.skip(input, residual=out, res_scale=_INV_SQRT2)      # (out + skip)/sqrt(2) in the skip's epilogue
 
 
 class ResBlock(nn.Module):
@@ -187,8 +207,9 @@ class ResBlock(nn.Module):
             out = self.conv2(c1[-2].forward_act_blur(h, c1[-1], c2[0]), start=1)
         else:
             out = self.conv2(self.conv1(input))
-        skip = input if self.skip is None else self.skip(input)
-        return add_scale(out, skip, _INV_SQRT2)
+        if self.skip is None:
+            return add_scale(out, input, _INV_SQRT2)
+        return self.skip(input, residual=out, res_scale=_INV_SQRT2)      # (out + skip)/sqrt(2) in the skip's epilogue
 
 
 class DisentanglementEncoder(nn.Module):

@@ -95,19 +95,23 @@ class EqualConv2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
-    def forward(self, input, activation: FusedLeakyReLU | None = None, stride: int | None = None):
+    def forward(self, input, activation: FusedLeakyReLU | None = None, stride: int | None = None, residual=None,
+                res_scale: float = 1.0):
         """``activation``: a FusedLeakyReLU module to fuse into the conv epilogue.  ``stride`` overrides the
-        module's stride (ConvLayer folds the decimation of a 1x1 stride-2 conv into the preceding blur)."""
+        module's stride (ConvLayer folds the decimation of a 1x1 stride-2 conv into the preceding blur).
+        ``residual``: merged in the epilogue, (conv(x) + bias + residual) * res_scale (activation-free only)."""
         k = self.weight.shape[2]
         stride = self.stride if stride is None else stride
         wp = packed_weight(self.weight, False, self.scale)
         if activation is not None:
             if self.bias is not None:
                 raise RuntimeError("EqualConv2d: a fused activation brings its own bias")
+            if residual is not None:
+                raise RuntimeError("EqualConv2d: residual merge is available without a fused activation only")
             return _ops.conv2d(input, wp, activation.bias, K=self.weight.shape[0], kh=k, kw=k, stride=stride,
                                pad=self.padding, act=True, alpha=activation.negative_slope, gain=activation.scale)
         return _ops.conv2d(input, wp, self.bias, K=self.weight.shape[0], kh=k, kw=k, stride=stride,
-                           pad=self.padding)
+                           pad=self.padding, residual=residual, res_scale=res_scale)
 
     def forward_act_blur(self, input, activation: FusedLeakyReLU, blur: "Blur"):
         """Blur(activation(conv(input))) with the fused backward of ``ConvActBlur``."""

@@ -125,10 +125,11 @@ class Geom(NamedTuple):
 
 
 # --------------------------------------------------------------------------- raw launches
-def _fwd(x, wp, g: Geom, in_scale=None, out_scale=None, bias=None, act=_lib.ACT_NONE, alpha=0.2, gain=1.0, impl=None):
+def _fwd(x, wp, g: Geom, in_scale=None, out_scale=None, bias=None, act=_lib.ACT_NONE, alpha=0.2, gain=1.0, impl=None,
+         residual=None, res_scale=1.0):
     y = empty_nhwc(g.N, g.K, g.OH, g.OW, x)
-    _lib.call("ideas_conv2d_forward", ptr(y), ptr(x), ptr(wp), ptr(in_scale), ptr(out_scale), ptr(bias),
-              g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, act, float(alpha), float(gain),
+    _lib.call("ideas_conv2d_forward_res", ptr(y), ptr(x), ptr(wp), ptr(in_scale), ptr(out_scale), ptr(bias), ptr(residual),
+              float(res_scale), g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, act, float(alpha), float(gain),
               DEFAULT_IMPL if impl is None else impl, stream_ptr(x))
     return y
 
@@ -200,14 +201,24 @@ class UnpackWeight(Function):
 
 # --------------------------------------------------------------------------- the three GEMMs
 class ConvFwd(Function):
+    """y = act(conv(x, w) + bias); with ``residual`` (same shape as y, activation-free convs only):
+    y = (conv(x, w) + bias + residual) * res_scale -- the residual merge of a ResBlock whose skip path ends in this
+    convolution (models.py:178,227), done in the convolution's epilogue."""
+
     @staticmethod
-    def forward(ctx, x, wp, bias, g: Geom, act, alpha, gain):
-        require_cuda(x, wp, bias)
+    def forward(ctx, x, wp, bias, g: Geom, act, alpha, gain, residual=None, res_scale=1.0):
+        require_cuda(x, wp, bias, residual)
         x = nhwc(x)
         _check(x, (g.N, g.C, g.H, g.W), "conv forward input")
         _check(wp, (g.kh * g.kw, g.K, g.C), "conv forward packed weight")
-        y = _fwd(x, wp, g, bias=bias, act=act, alpha=alpha, gain=gain)
+        if residual is not None:
+            if act != _lib.ACT_NONE:
+                raise RuntimeError("conv forward: a residual operand is merged after activation-free convolutions only")
+            residual = nhwc(residual)
+            _check(residual, (g.N, g.K, g.OH, g.OW), "conv forward residual")
+        y = _fwd(x, wp, g, bias=bias, act=act, alpha=alpha, gain=gain, residual=residual, res_scale=res_scale)
         ctx.g, ctx.act, ctx.alpha, ctx.gain, ctx.has_bias = g, act, alpha, gain, bias is not None
+        ctx.res_scale = res_scale if residual is not None else None
         ctx.save_for_backward(x, wp, y if act != _lib.ACT_NONE else None)
         return y
 
@@ -216,14 +227,17 @@ class ConvFwd(Function):
         x, wp, out = ctx.saved_tensors
         g = ctx.g
         want_bias = ctx.has_bias and ctx.needs_input_grad[2]
-        gb = None
+        gb = gres = None
+        if ctx.res_scale is not None:
+            gy = gy * ctx.res_scale                    # one pass serves the residual branch and this convolution
+            gres = gy if ctx.needs_input_grad[7] else None
         if ctx.act != _lib.ACT_NONE:
             gy, gb = FusedLeakyReLUFunctionBackward.apply(gy, out, want_bias, ctx.alpha, ctx.gain)
         elif want_bias:
             gb = gy.sum(dim=(0, 2, 3))
         gx = ConvDgrad.apply(gy, wp, g) if ctx.needs_input_grad[0] else None
         gw = ConvWgrad.apply(x, gy, g) if ctx.needs_input_grad[1] else None
-        return gx, gw, (gb if want_bias else None), None, None, None, None
+        return gx, gw, (gb if want_bias else None), None, None, None, None, gres, None
 
 
 class ConvDgrad(Function):
@@ -315,10 +329,12 @@ class ConvActBlur(Function):
         return gx, gw, gb, None, None, None, None, None
 
 
-def conv2d(x, wp, bias=None, *, K, kh, kw, stride=1, pad=0, act=False, alpha=0.2, gain=2 ** 0.5):
-    """y = [lrelu](conv(x, w) + bias) with packed weights (see PackWeight)."""
+def conv2d(x, wp, bias=None, *, K, kh, kw, stride=1, pad=0, act=False, alpha=0.2, gain=2 ** 0.5, residual=None,
+           res_scale=1.0):
+    """y = [lrelu](conv(x, w) + bias) with packed weights (see PackWeight); optionally (.. + residual) * res_scale."""
     g = Geom.forward(x.shape, K, kh, kw, stride, pad)
-    return ConvFwd.apply(x, wp, bias, g, _lib.ACT_LRELU if act else _lib.ACT_NONE, alpha, gain if act else 1.0)
+    return ConvFwd.apply(x, wp, bias, g, _lib.ACT_LRELU if act else _lib.ACT_NONE, alpha, gain if act else 1.0, residual,
+                         res_scale)
 
 
 def conv_transpose2d(x, wp, *, C_out, kh, kw, stride=1, pad=0):

@@ -21,7 +21,13 @@ def _out_size(n, up, down, p0, p1, k):
     return (n * up + p0 + p1 - k) // down + 1
 
 
-def _run(x, kernel, up, down, pad, bias=None, alpha=0.2, gain=1.0):
+def residual_ok(x, kernel, up, down) -> bool:
+    """Whether ideas_upfirdn2d_res can merge a residual for these parameters (its fused up-sampling path)."""
+    return tuple(up) == (2, 2) and tuple(down) == (1, 1) and kernel.shape[0] <= 4 and kernel.shape[1] <= 4 and \
+        x.shape[1] % 4 == 0 and x.shape[0] <= 65535
+
+
+def _run(x, kernel, up, down, pad, bias=None, alpha=0.2, gain=1.0, residual=None, res_scale=1.0):
     """x: NHWC-dense (N,C,H,W) tensor.  pad = (x0, x1, y0, y1)."""
     n, c, h, w = x.shape
     kh, kw = kernel.shape
@@ -30,8 +36,11 @@ def _run(x, kernel, up, down, pad, bias=None, alpha=0.2, gain=1.0):
     if n > 0 and (oh < 1 or ow < 1):
         raise RuntimeError(f"upfirdn2d: non-positive output size {oh}x{ow}")
     out = empty_nhwc(n, c, max(oh, 0), max(ow, 0), x)
-    _lib.call("ideas_upfirdn2d", ptr(out), ptr(x), ptr(kernel), n, h, w, c, kh, kw, up[0], up[1], down[0], down[1],
-              pad[0], pad[1], pad[2], pad[3], ptr(bias), float(alpha), float(gain), stream_ptr(x))
+    if residual is not None and tuple(residual.shape) != tuple(out.shape):
+        raise RuntimeError(f"upfirdn2d: residual shape {tuple(residual.shape)} != output shape {tuple(out.shape)}")
+    _lib.call("ideas_upfirdn2d_res", ptr(out), ptr(x), ptr(kernel), n, h, w, c, kh, kw, up[0], up[1], down[0], down[1],
+              pad[0], pad[1], pad[2], pad[3], ptr(bias), float(alpha), float(gain), ptr(residual), float(res_scale),
+              stream_ptr(x))
     return out
 
 
@@ -63,23 +72,30 @@ class UpFirDn2dBackward(Function):
 
 
 class UpFirDn2d(Function):
+    """out = upfirdn2d(input); with ``residual`` (out-shaped): out = (upfirdn2d(input) + residual) * res_scale."""
+
     @staticmethod
-    def forward(ctx, input, kernel, up, down, pad):
-        require_cuda(input, kernel)
+    def forward(ctx, input, kernel, up, down, pad, residual=None, res_scale=1.0):
+        require_cuda(input, kernel, residual)
         kernel = kernel.contiguous()
         x = nhwc(input)
-        out = _run(x, kernel, up, down, pad)
+        out = _run(x, kernel, up, down, pad, residual=nhwc(residual) if residual is not None else None, res_scale=res_scale)
         ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
         ctx.cfg = (up, down, pad, tuple(input.shape), (out.shape[2], out.shape[3]))
+        ctx.res_scale = res_scale if residual is not None else None
         return out
 
     @staticmethod
     def backward(ctx, grad_output):
         kernel, grad_kernel = ctx.saved_tensors
         up, down, pad, in_size, out_size = ctx.cfg
+        gres = None
+        if ctx.res_scale is not None:
+            grad_output = grad_output * ctx.res_scale
+            gres = grad_output if ctx.needs_input_grad[5] else None
         g_pad = _grad_pad(in_size[2:], out_size, kernel.shape, up, down, pad)
         gx = UpFirDn2dBackward.apply(grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size)
-        return gx, None, None, None, None
+        return gx, None, None, None, None, gres, None
 
 
 class BlurBiasAct(Function):
@@ -108,8 +124,9 @@ class BlurBiasAct(Function):
         return gx, None, None, (gb if ctx.needs_input_grad[3] else None), None, None
 
 
-def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
-    return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0), residual=None, res_scale=1.0):
+    """Reference signature (upfirdn2d.py:145) plus an optional residual merged into the result (see UpFirDn2d)."""
+    return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]), residual, res_scale)
 
 
 def blur_bias_act(input, kernel, pad, bias, negative_slope=0.2, scale=2 ** 0.5):

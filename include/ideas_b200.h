@@ -109,6 +109,16 @@ int ideas_upfirdn2d(float* out, const float* x, const float* kernel,
                     int up_x, int up_y, int down_x, int down_y,
                     int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                     const float* bias, float alpha, float gain, void* stream);
+/* Same with a residual merged into the result: out = (upfirdn2d(x) + residual) * res_scale, `residual` of out's
+ * shape.  Served by the fused up-sampling path only (up = 2, down = 1, <= 4x4 kernel, channels % 4 == 0, no bias):
+ * the (out + skip)/sqrt(2) of an up-sampling residual block, whose skip path ends in this blur (models.py:78-95,
+ * :178).  Other parameter sets return IDEAS_ERR_UNSUPPORTED. */
+int ideas_upfirdn2d_res(float* out, const float* x, const float* kernel,
+                        int major, int in_h, int in_w, int minor, int kernel_h, int kernel_w,
+                        int up_x, int up_y, int down_x, int down_y,
+                        int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                        const float* bias, float alpha, float gain,
+                        const float* residual, float res_scale, void* stream);
 
 /* Backward of the pair  y = act(u) -> z = Blur(y)  (conv1 -> FusedLeakyReLU -> Blur of a down-sampling
  * ResBlock, reference models.py:213-227) in one pass:

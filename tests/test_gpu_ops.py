@@ -508,3 +508,54 @@ def test_equal_linear_first_and_second_order_vs_oracle():
     assert rel(yc, yr) <= 2e-6
     for a, c, name in zip(got, want, ("dW", "db", "dx")):
         assert rel(a, c) <= 2e-5, (name, rel(a, c))
+
+
+@pytest.mark.parametrize("shape,pad", [((2, 8, 9, 7), (2, 0)), ((3, 64, 16, 16), (2, 0)), ((2, 12, 5, 6), (1, 1))])
+def test_upfirdn2d_up2_residual_merge(op, shape, pad):
+    """(upfirdn2d(x, up=2) + residual) * s in the up-sampling kernel's epilogue (ideas_upfirdn2d_res) vs the two-step
+    composition, values and both gradients."""
+    from ideas_b200.stylegan2.model import make_kernel
+    g = torch.Generator().manual_seed(2)
+    k = (make_kernel([1, 3, 3, 1]) * 4).cuda()
+    x = torch.randn(*shape, generator=g).cuda().requires_grad_(True)
+    want0 = op.upfirdn2d(x, k, up=2, pad=pad)
+    res = torch.randn(*want0.shape, generator=g).cuda().requires_grad_(True)
+    s = 2 ** -0.5
+    want = (want0 + res) * s
+    got = op.upfirdn2d(x, k, up=2, pad=pad, residual=res, res_scale=s)
+    gy = torch.randn(*want.shape, generator=g).cuda()
+    wg = torch.autograd.grad(want, [x, res], gy)
+    gg = torch.autograd.grad(got, [x, res], gy)
+    assert rel(got, want) <= 1e-6
+    for a, b in zip(gg, wg):
+        assert rel(a, b) <= 1e-6
+
+
+def test_conv2d_residual_merge_autograd(conv_mode):
+    """conv2d(..., residual=r, res_scale=s) == (conv2d(..) + r) * s with gradients to x, w, bias and r, first and second
+    order (the discriminators' ResBlocks are differentiated twice by R1)."""
+    from ideas_b200.stylegan2.op import conv as C
+    g = torch.Generator().manual_seed(4)
+    N, Cc, K, H = 2, 32, 64, 12
+    x = torch.randn(N, Cc, H, H, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(K, Cc, 1, 1, generator=g) / Cc ** 0.5).cuda().requires_grad_(True)
+    b = torch.randn(K, generator=g).cuda().requires_grad_(True)
+    r = torch.randn(N, K, H, H, generator=g).cuda().requires_grad_(True)
+    s = 2 ** -0.5
+
+    def run(fused):
+        wp = C.PackWeight.apply(w, False, 1.0)
+        if fused:
+            y = C.conv2d(x, wp, b, K=K, kh=1, kw=1, residual=r, res_scale=s)
+        else:
+            y = (C.conv2d(x, wp, b, K=K, kh=1, kw=1) + r) * s
+        (gx,) = torch.autograd.grad(y.pow(2).sum(), x, create_graph=True)
+        pen = gx.pow(2).sum()
+        return y, torch.autograd.grad(pen + y.sum(), [x, w, b, r])
+
+    y0, g0 = run(False)
+    y1, g1 = run(True)
+    tol = 1e-5 if conv_mode == "fp32" else 2e-3
+    assert T.rel(y1, y0) <= tol
+    for a, c in zip(g1, g0):
+        assert T.rel(a, c) <= tol * 5

@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--case", default=None, help="run ONE roofline kernel alone (for ncu); see CASES in bench.py")
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--no-batch-g", action="store_true", help="A/B: three Generator calls per phase instead of one batched call")
+    ap.add_argument("--batch-g", action="store_true", help="A/B: one batched Generator call per phase instead of three")
+    ap.add_argument("--split-dreal", action="store_true", help="A/B: Dreal on the three fake batches separately")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--prune-dead-backward", action="store_true",
                     help="NOT the default measurement: restrict the loop's second backward (train.py:214-216) to Ex's parameters")
@@ -415,7 +416,7 @@ def run_ours(args):
     B, S = args.batch, args.image_size
     targs = default_args(batch_size=B, image_size=S)
     tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
-                 prune_dead_backward=args.prune_dead_backward, batch_generator=not args.no_batch_g)
+                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=args.split_dreal)
     tr.broadcast_parameters(0)
     import random
     torch.manual_seed(1000 + rank)                   # per-rank data / Z / T2 / crops

@@ -78,9 +78,10 @@ class Trainer:
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
-                 prune_dead_backward: bool = False, batch_generator: bool = False):
+                 prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = False):
         self.args = args
         self.batch_generator = bool(batch_generator)
+        self.split_dreal = bool(split_dreal) and not self.batch_generator
         self.device = torch.device(device)
         self.cuda_graphs = bool(cuda_graphs and self.device.type == "cuda")
         # independent sub-graphs of one iteration (Dreal on the real batch, the co-occurrence branch, the
@@ -314,9 +315,15 @@ class Trainer:
         126 MB L2, and the E(container) branch can no longer start under the third call.  Off by default."""
         if not self.batch_generator:
             xs = self.nets["G"](S1, T1), self.nets["G"](S2, T1), self.nets["G"](S2, T2)
-            return xs, torch.cat(xs, 0)
+            return xs, (None if self.split_dreal else torch.cat(xs, 0))
         hat = self.nets["G"](torch.cat((S1, S2, S2), 0), torch.cat((T1, T1, T2), 0))
         return hat.chunk(3, 0), hat
+
+    def _dreal_fake(self, x1, x2, x3, x_all):
+        """Dreal(cat(hat_X1, hat_X2, hat_X3)) (train.py:73,161); per-sample independent, so optionally three calls."""
+        if x_all is not None:
+            return self.nets["Dreal"](x_all)
+        return torch.cat([self.nets["Dreal"](x) for x in (x1, x2, x3)], 0)
 
     def _iteration(self, X, r1, late, draws, boxes, device_rng) -> Dict[str, torch.Tensor]:
         a, t = self.args, self.nets
@@ -350,7 +357,7 @@ class Trainer:
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_d")
         (hat_X1, hat_X2, hat_X3), hat_all = self._generate3(S1, S2, T1, T2)
-        fake_pred = t["Dreal"](hat_all)
+        fake_pred = self._dreal_fake(hat_X1, hat_X2, hat_X3, hat_all)
         fake_patch = patchify_image(hat_X2, a.n_crop, crops=fake_boxes)
         self._join(1, real_texture_pred, ref_input, real_patch, ref_patch)
         fake_texture_pred, _ = t["Dco"](fake_patch, ref_input=ref_input)
@@ -401,7 +408,7 @@ class Trainer:
             fake_patch_pred, _ = t["Dco"](fake_patch, ref_patch, ref_batch=a.ref_crop)
             G_texture_loss = g_nonsaturating_loss(fake_patch_pred)
         G_rec_loss = F.l1_loss(hat_X1, X)
-        G_real_loss = g_nonsaturating_loss(t["Dreal"](hat_all))
+        G_real_loss = g_nonsaturating_loss(self._dreal_fake(hat_X1, hat_X2, hat_X3, hat_all))
         E_dist_loss = g_nonsaturating_loss(t["Ddist"](T1))
         self._join(0, E_stru_loss, Ex_loss)
         self._join(1, G_texture_loss)

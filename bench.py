@@ -506,6 +506,13 @@ def run_ours(args):
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     line["config"]["peak_mem_gib"] = round(peak_mem, 2)
     if world > 1:
+        # every rank started from rank 0's weights and applied the same all-reduced gradients: the replicas must be
+        # bit-identical after the run
+        cs = tr.replica_checksum()
+        gathered = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(gathered, cs)
+        line["replicas_identical"] = bool(all(torch.equal(gathered[0], g) for g in gathered))
+        line["config"]["grad_allreduce"] = "in-place flat fp32 bucket per optimiser (grads are views), NCCL sum / world"
         dist.barrier()
     if rank == 0:
         if world == 1:
@@ -525,14 +532,20 @@ def run_ours(args):
                                                   f"({'unmodified reference' if kind == 'reference' else 'oracle port of train.py:33-221'}), {t:.1f} s each"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        # The captured graphs hold NCCL work: tearing the communicator down while they are alive can block at
-        # exit (observed: the JSON line printed, then destroy_process_group never returned).  Everything is
-        # measured and printed; leave together and skip the teardown.
-        dist.barrier()
-        torch.cuda.synchronize()
+        # Orderly teardown: the captured graphs hold NCCL work, so they go first, then the communicator.  A watchdog
+        # still ends the process if the teardown blocks (round 1 observed destroy_process_group hanging with live
+        # graphs) -- everything has been measured and printed by now.
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        dist.barrier()
+        tr.close()
+        del tr
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def main():

@@ -37,6 +37,7 @@ namespace {
 // drops the low 13 mantissa bits, a truncation that biases every product low: measured on B200 at
 // K = 4608, max rel error vs fp64 7.5e-4 (signed bias -7.1e-4) truncated vs 3.0e-4 (bias -1e-5) rounded.
 std::atomic<int> g_tma_tf32{1};
+std::atomic<int> g_tail_split{1};     // option "tail_split": balance the last round of the pixel-major kernel (launch_fwd)
 
 constexpr int kThreads = 192;
 constexpr int kBlockM = 128;   // pixels per sub-tile == UMMA M
@@ -64,6 +65,7 @@ struct alignas(64) FwdParams {
   int o_s, o_py, o_px;
   int bw, bh, bn;
   int tiles_x, tiles_y, subtiles;
+  int full_pairs;   // CTAs with blockIdx.y < full_pairs own two sub-tiles, the rest one (tail balancing, launch_fwd)
   int ntaps, csteps;
   int act;
   float alpha, gain;
@@ -95,10 +97,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
   // sub-tile origins
   int qx0[kSub], qy0[kSub], n0[kSub];
   bool sub_ok[kSub];
+  const bool pair = (int)blockIdx.y < p.full_pairs;
+  const int nsub = pair ? kSub : 1;
+  const int first = pair ? (int)blockIdx.y * kSub : p.full_pairs * kSub + ((int)blockIdx.y - p.full_pairs);
 #pragma unroll
   for (int j = 0; j < kSub; ++j) {
-    const int id = blockIdx.y * kSub + j;
-    sub_ok[j] = id < p.subtiles;
+    const int id = first + j;
+    sub_ok[j] = j < nsub && id < p.subtiles;
     const int bx = id % p.tiles_x;
     const int t = id / p.tiles_x;
     qx0[j] = bx * p.bw;
@@ -132,11 +137,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
         const TapU tp = p.taps[t];
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
         const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-        ptx::mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+        ptx::mbar_arrive_expect_tx(fb, (uint32_t)nsub * kABytes + Cfg::kBBytes);
         const uint32_t sa = tiles + stage * Cfg::kStageBytes;
 #pragma unroll
         for (int j = 0; j < kSub; ++j)
-          ptx::tma_load_4d(sa + j * kABytes, &p.src[tp.map], fb, c0, qx0[j] + tp.ox, qy0[j] + tp.oy, n0[j]);
+          if (j < nsub) ptx::tma_load_4d(sa + j * kABytes, &p.src[tp.map], fb, c0, qx0[j] + tp.ox, qy0[j] + tp.oy, n0[j]);
         ptx::tma_load_3d(sa + kSub * kABytes, &p.w, fb, c0, k0, tp.widx);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
         const uint64_t bdesc = ptx::smem_desc_sw128(sa + kSub * kABytes, 16, 1024);
 #pragma unroll
         for (int j = 0; j < kSub; ++j) {
+          if (j >= nsub) break;
           const uint64_t adesc = ptx::smem_desc_sw128(sa + j * kABytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
@@ -172,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
     ptx::tc_fence_after();
 #pragma unroll
     for (int j = 0; j < kSub; ++j) {
+      if (j >= nsub) break;
       const int wq = row % p.bw;
       const int t = row / p.bw;
       const int qx = qx0[j] + wq, qy = qy0[j] + (t % p.bh), n = n0[j] + t / p.bh;
@@ -293,8 +300,23 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
     attr_err = cudaFuncSetAttribute(conv_umma_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma: cudaFuncSetAttribute");
-  dim3 grid(ntiles_n, ceil_div(p.subtiles, kSub));
-  conv_umma_fwd_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(p);
+  // Tail balancing: one CTA per SM (the tiles fill shared memory), so a grid of T CTAs runs in ceil(T / 148)
+  // rounds.  When the last round would be less than half full, its CTAs are given ONE 128-pixel sub-tile instead
+  // of two -- twice as many CTAs of half the length, i.e. the tail costs ~half a round (cfg 3 at batch 16: 512
+  // CTAs = 3.46 rounds -> 444 pairs + 136 singles = 3.5 instead of 4).
+  const int pf = p.subtiles / kSub;                       // complete pairs; an odd last sub-tile is a single anyway
+  int full_pairs = pf;
+  const int total = (pf + (p.subtiles - pf * kSub)) * ntiles_n;
+  const int tail = total % kNumSMs;
+  if (total > kNumSMs && tail > 0 && tail <= kNumSMs / 2 && g_tail_split.load()) {
+    int cp = ceil_div(tail, ntiles_n);
+    cp = cp > pf ? pf : cp;
+    full_pairs = pf - cp;
+  }
+  FwdParams q = p;
+  q.full_pairs = full_pairs;
+  dim3 grid(ntiles_n, full_pairs + (p.subtiles - full_pairs * kSub));
+  conv_umma_fwd_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(q);
   IDEAS_CHECK_LAUNCH("conv_umma_fwd");
   return IDEAS_OK;
 }
@@ -1507,6 +1529,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "halo")) {
     ideas::g_halo_mode.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "tail_split")) {
+    ideas::g_tail_split.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "pmh")) {

@@ -33,7 +33,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, bound=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from ideas_b200.train_step import FlatGradAllReduce
@@ -42,6 +42,9 @@ def _worker(rank, world, port, out):
     opt = torch.optim.Adam(net.parameters(), lr=1e-2, betas=(0.0, 0.99))
     red = FlatGradAllReduce(list(net.parameters()))
     opt.register_step_pre_hook(red)
+    if bound:                      # grads become views into the flat bucket; zero_grad must keep them
+        red.bind()
+        opt.zero_grad = lambda *a, **k: red.zero()
     g = torch.Generator().manual_seed(123)
     X = torch.randn(8, 6, generator=g)
     Y = torch.randn(8, 1, generator=g)
@@ -91,6 +94,16 @@ def test_flat_allreduce_world2(tmp_path):
     assert r["calls"] == 6
     assert torch.equal(r["params"][0], r["params"][1])                     # replicas stay identical
     assert torch.allclose(r["params"][0], _single(), atol=1e-6, rtol=1e-5)  # == big-batch training
+
+
+def test_flat_allreduce_in_place_bucket_world2(tmp_path):
+    """bind(): p.grad are views into the bucket, autograd accumulates in place, the all-reduce needs no copies."""
+    out = str(tmp_path / "dp_bound.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out, True), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["calls"] == 6
+    assert torch.equal(r["params"][0], r["params"][1])
+    assert torch.allclose(r["params"][0], _single(), atol=1e-6, rtol=1e-5)
 
 
 def test_flat_allreduce_is_noop_without_process_group():

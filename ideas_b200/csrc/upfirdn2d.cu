@@ -94,6 +94,11 @@ __device__ __forceinline__ void blur_epilogue(float4& v, const float4& b4, const
     v.z = (r.z > 0.f ? v.z : v.z * p.alpha) * p.gain;
     v.w = (r.w > 0.f ? v.w : v.w * p.alpha) * p.gain;
     bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+  } else if (EPI == 3) {
+    // backward of  u -> d[n,c] * u -> Blur: v = blur^T(g); dot[n,c] += sum_p v * u (r = u), result = v * d (b4 = d)
+    bsum.x = fmaf(v.x, r.x, bsum.x); bsum.y = fmaf(v.y, r.y, bsum.y);
+    bsum.z = fmaf(v.z, r.z, bsum.z); bsum.w = fmaf(v.w, r.w, bsum.w);
+    v.x *= b4.x; v.y *= b4.y; v.z *= b4.z; v.w *= b4.w;
   }
 }  // already flipped and zero-extended: k[ky][kx] meets in[oy+ky-pad][ox+kx-pad]
 
@@ -131,7 +136,8 @@ __device__ __forceinline__ void blur4_general(float* __restrict__ out, const flo
   const int64_t orow = (int64_t)p.out_w * p.minor;
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (EPI == 1) b4 = *reinterpret_cast<const float4*>(bias + c);
-  const float* refp = EPI == 2 ? ref + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c : nullptr;
+  if (EPI == 3) b4 = bias ? *reinterpret_cast<const float4*>(bias + (int64_t)m * p.minor + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float* refp = EPI >= 2 ? ref + (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c : nullptr;
 
   bool colok[XT + 3];
 #pragma unroll
@@ -179,7 +185,7 @@ __device__ __forceinline__ void blur4_general(float* __restrict__ out, const flo
       s0[j] = h[0];
       if (oy >= oy0 && ox0 + j < p.out_w) {
         float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI == 2) rv = ld_stream4(refp + (int64_t)oy * orow + (int64_t)j * p.minor);
+        if (EPI >= 2) rv = ld_stream4(refp + (int64_t)oy * orow + (int64_t)j * p.minor);
         blur_epilogue<EPI>(done, b4, p, rv, bsum);
         st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, done);
       }
@@ -258,7 +264,7 @@ __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const floa
 #pragma unroll
         for (int j = 0; j < XT; ++j) {
           refv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (EPI == 2 && oy >= oy0 && (INTERIOR || ox0 + j < p.out_w)) refv[j] = ld_stream4(refp + (op - o) + (int64_t)j * p.minor);
+          if (EPI >= 2 && oy >= oy0 && (INTERIOR || ox0 + j < p.out_w)) refv[j] = ld_stream4(refp + (op - o) + (int64_t)j * p.minor);
         }
 #pragma unroll
         for (int j = 0; j < XT; ++j) {
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(128) blur4_nhwc_kernel(float* __restrict__ out
                                                          const float* __restrict__ kernel,
                                                          const float* __restrict__ bias, UpfirdnParams p,
                                                          const float* __restrict__ ref, float* __restrict__ gbias) {
-  __shared__ float4 red[EPI == 2 ? 128 : 1];
+  __shared__ float4 red[EPI >= 2 ? 128 : 1];
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   // taps: flipped (true convolution) and zero-extended to 4x4; 16 uniform loads per thread
   Taps4 tp;
@@ -331,15 +337,17 @@ __global__ void __launch_bounds__(128) blur4_nhwc_kernel(float* __restrict__ out
     const float* xin = x + (int64_t)m * p.in_h * p.in_w * p.minor + c;
     const int64_t obase = (((int64_t)m * p.out_h) * p.out_w + ox0) * p.minor + c;
     float* o = out + obase;
-    const float* refp = EPI == 2 ? ref + obase : nullptr;
+    const float* refp = EPI >= 2 ? ref + obase : nullptr;
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (EPI == 1) b4 = *reinterpret_cast<const float4*>(bias + c);
+    if (EPI == 3) b4 = bias ? *reinterpret_cast<const float4*>(bias + (int64_t)m * p.minor + c) : make_float4(1.f, 1.f, 1.f, 1.f);
     const bool interior = ix0 >= 0 && ix0 + XT + 3 <= p.in_w && ox0 + XT <= p.out_w && oy0 - p.pad_y0 >= 0 &&
                           oy1 - 1 - p.pad_y0 + 3 < p.in_h;
     if (interior) blur4sep_strip<XT, EPI, true>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum);
     else blur4sep_strip<XT, EPI, false>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum);
   }
-  if (EPI == 2 && gbias != nullptr) {
+  if (EPI >= 2 && gbias != nullptr) {
+    if (EPI == 3) gbias += (int64_t)blockIdx.z * p.minor;      // per-(image, channel) sums
     // bias gradient: fold the replicas of each channel group inside the CTA (blockDim is a multiple of c4n or
     // c4n a multiple of blockDim: thread t always owns channel group (blockIdx.x*128 + t) % c4n), then one
     // atomic per channel per CTA
@@ -716,6 +724,7 @@ extern "C" int ideas_blur_act_backward(float* gx, float* gbias, const float* g, 
   p.out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
   p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
   p.alpha = alpha; p.gain = gain;
+  p.residual = nullptr; p.res_scale = 1.f;
   IDEAS_REQUIRE(p.out_h >= 1 && p.out_w >= 1, "blur_act_backward: padding/cropping leaves no output");
   if (major == 0) return IDEAS_OK;
   IDEAS_REQUIRE(gx && g && ref && kernel, "blur_act_backward: null pointer");
@@ -730,5 +739,42 @@ extern "C" int ideas_blur_act_backward(float* gx, float* gbias, const float* g, 
   dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
   blur4_nhwc_kernel<ROWS, XT, 2><<<grid, 128, 0, st>>>(gx, g, kernel, nullptr, p, ref, gbias);
   IDEAS_CHECK_LAUNCH("blur_act_backward");
+  return IDEAS_OK;
+}
+
+// Backward of  u -> d[n,c] * u -> Blur  (the demodulated, up-sampled branch of ModulatedConv2d, stylegan2/model.py:250-261)
+// in one pass over the incoming gradient g:  v = blur^T(g)  (caller-supplied flipped kernel and gradient pads),
+//   gx[n,p,c] = v * scale[n,c]        (scale = d, may be NULL = 1)
+//   dot[n,c] += sum_p v[n,p,c] * ref[n,p,c]        (ref = u, shape of gx; dot zero-initialised by the caller)
+// so that dL/dd = dot / d.  Replaces UpFirDn2dBackward followed by a channel_dot pass: the blurred gradient is never written.
+extern "C" int ideas_blur_scale_dot_backward(float* gx, float* dot, const float* g, const float* ref, const float* scale,
+                                             const float* kernel, int major, int in_h, int in_w, int minor,
+                                             int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                                             void* stream) {
+  const float alpha = 0.f, gain = 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  IDEAS_REQUIRE(major >= 0 && in_h >= 1 && in_w >= 1 && minor >= 1, "blur_scale_dot_backward: bad input shape");
+  IDEAS_REQUIRE(kernel_h >= 1 && kernel_w >= 1, "blur_scale_dot_backward: empty FIR kernel");
+  UpfirdnParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
+  p.up_x = p.up_y = p.down_x = p.down_y = 1; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
+  p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
+  p.alpha = alpha; p.gain = gain;
+  p.residual = nullptr; p.res_scale = 1.f;
+  IDEAS_REQUIRE(p.out_h >= 1 && p.out_w >= 1, "blur_scale_dot_backward: padding/cropping leaves no output");
+  if (major == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(gx && g && ref && kernel, "blur_scale_dot_backward: null pointer");
+  const int c4n = minor / 4;
+  const bool fast = kernel_h <= 4 && kernel_w <= 4 && minor % 4 == 0 && aligned16(gx) && aligned16(g) && aligned16(ref) && (!scale || aligned16(scale)) &&
+                    major <= 65535 && (c4n <= 128 ? 128 % c4n == 0 : c4n % 128 == 0);
+  if (!fast) {
+    set_error("blur_scale_dot_backward: needs a <= 4x4 kernel, channels %% 4 == 0 and a power-of-two channel count (C=%d)", minor);
+    return IDEAS_ERR_UNSUPPORTED;
+  }
+  constexpr int ROWS = 32, XT = 2;
+  dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
+  blur4_nhwc_kernel<ROWS, XT, 3><<<grid, 128, 0, st>>>(gx, g, kernel, scale, p, ref, dot);
+  IDEAS_CHECK_LAUNCH("blur_scale_dot_backward");
   return IDEAS_OK;
 }

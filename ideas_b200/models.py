@@ -178,7 +178,15 @@ class StyledResBlock(nn.Module):
     def forward(self, input, style, noise=None, modulation=None):
         """``modulation``: optional (s1, s2), the outputs of conv1 / conv2's modulation linears."""
         m1, m2 = modulation if modulation is not None else (None, None)
-        out = self.conv2(self.conv1(input, style, noise, modulation=m1), style, noise, modulation=m2)
+        if input.is_cuda:
+            # conv1 hands conv2 its input already multiplied by conv2's style (s2 * a): conv2 runs no modulation
+            # pass, and its style gradient comes out of conv1's activation backward for free (op/conv.py, ``post``)
+            if m2 is None:
+                m2 = self.conv2.conv.modulation(style)
+            _, a_mod = self.conv1(input, style, noise, modulation=m1, post_modulation=m2)
+            out = self.conv2(a_mod, style, noise, modulation=m2, premodulated=True)
+        else:
+            out = self.conv2(self.conv1(input, style, noise, modulation=m1), style, noise, modulation=m2)
         if self.skip is None:
             return add_scale(out, input, _INV_SQRT2)
         return self.skip(input, residual=out, res_scale=_INV_SQRT2)      # (out + skip)/sqrt(2) in the skip's epilogue

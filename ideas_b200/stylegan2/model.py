@@ -197,11 +197,15 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
-    def forward(self, input, style, activation: FusedLeakyReLU | None = None, modulation: torch.Tensor | None = None):
+    def forward(self, input, style, activation: FusedLeakyReLU | None = None, modulation: torch.Tensor | None = None,
+                premodulated: bool = False, post_modulation: torch.Tensor | None = None):
         """Returns the modulated convolution; with ``activation`` the FusedLeakyReLU (bias,
         slope, gain) is applied inside the same kernels (StyledConv passes its own).  ``modulation``: the
         per-sample channel scales s = self.modulation(style), when the caller has already computed them (the
-        Generator evaluates the modulation linears of all its layers in one GEMM)."""
+        Generator evaluates the modulation linears of all its layers in one GEMM).
+        ``premodulated``: ``input`` is already s * x (written by the producing layer, below).
+        ``post_modulation`` (B, Cout): also return out * post_modulation, the next layer's pre-modulated input --
+        the result is then the pair (out, out_modulated)."""
         k = self.kernel_size
         if input.is_cuda:
             # layout conversion OUTSIDE the autograd nodes below: they save their inputs for the double backward
@@ -223,16 +227,20 @@ class ModulatedConv2d(nn.Module):
         alpha = activation.negative_slope if act else 0.2
         gain = activation.scale if act else 1.0
         if self.upsample:
+            if premodulated:
+                raise RuntimeError("ModulatedConv2d: the up-sampling branch modulates its own input")
             g = Geom.transposed(input.shape, self.out_channel, k, k, 2, 0)
             pad = self.blur.pad
             return ModConvUp.apply(input, s, d, wp, self.blur.kernel, (pad[0], pad[1], pad[0], pad[1]), bias, g,
-                                   act, alpha, gain)
+                                   act, alpha, gain, post_modulation)
         if self.downsample:
+            if premodulated:
+                raise RuntimeError("ModulatedConv2d: the down-sampling branch modulates its own input")
             input = self.blur(input)
             g = Geom.forward(input.shape, self.out_channel, k, k, 2, 0)
         else:
             g = Geom.forward(input.shape, self.out_channel, k, k, 1, self.padding)
-        return ModConv.apply(input, s, d, wp, bias, g, act, alpha, gain)
+        return ModConv.apply(input, s, d, wp, bias, g, act, alpha, gain, premodulated, post_modulation)
 
 
 class NoiseInjection(nn.Module):
@@ -283,8 +291,9 @@ class StyledConv_without_noise(nn.Module):
                                     blur_kernel=blur_kernel, demodulate=demodulate)
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward(self, input, style, noise=None, modulation=None):
-        return self.conv(input, style, activation=self.activate, modulation=modulation)
+    def forward(self, input, style, noise=None, modulation=None, premodulated=False, post_modulation=None):
+        return self.conv(input, style, activation=self.activate, modulation=modulation, premodulated=premodulated,
+                         post_modulation=post_modulation)
 
 
 class ToRGB(nn.Module):

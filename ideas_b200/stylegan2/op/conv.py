@@ -359,7 +359,7 @@ def _act_or_bias(z, bias, act, alpha, gain):
 def _modconv_composite(x, s, d, wp, bias, g: Geom, act, alpha, gain):
     """ModConv written with the differentiable building blocks (each has a double backward): used to differentiate
     the backward itself (create_graph=True: path-length regularisation, stylegan2/train.py:85-98)."""
-    xm = x * s.view(g.N, g.C, 1, 1)
+    xm = x if s is None else x * s.view(g.N, g.C, 1, 1)          # s None: x is already modulated
     u = ConvFwd.apply(xm, wp, None, g, _lib.ACT_NONE, 0.2, 1.0)
     if d is not None:
         u = u * d.view(g.N, g.K, 1, 1)
@@ -387,9 +387,42 @@ def _grad_of_composite(fn, tensors, needs, gy):
         alias = [t.view_as(t) if (t is not None and t.requires_grad) else t for t in tensors]
         out = fn(*alias)
         wanted = [a for a, n in zip(alias, needs) if n and a is not None and a.requires_grad]
-        grads = torch.autograd.grad(out, wanted, gy, create_graph=True, allow_unused=True) if wanted else ()
+        outs, gys = (list(out), list(gy)) if isinstance(out, tuple) else ([out], [gy])
+        grads = torch.autograd.grad(outs, wanted, gys, create_graph=True, allow_unused=True) if wanted else ()
     it = iter(grads)
     return [next(it) if (n and t is not None and t.requires_grad) else None for t, n in zip(tensors, needs)]
+
+
+def _scale_channels(x, sc, n, p, c):
+    out = torch.empty_like(x)
+    _lib.call("ideas_scale_channels", ptr(out), ptr(x), ptr(sc), n, p, c, stream_ptr(x))
+    return out
+
+
+def _post_general(gy, gym, out, post, n, p, c):
+    """Both outputs of a post-modulating layer were used: fold the gradient of out*post into the gradient of out.
+    Returns (gy_total, g_post) with g_post[n,c] = sum_p gym * out."""
+    g_post = torch.zeros((n, c), device=out.device, dtype=out.dtype)
+    tmp = torch.empty_like(out)
+    _lib.call("ideas_channel_dot", ptr(g_post), ptr(tmp), ptr(out), ptr(nhwc(gym)), ptr(post), n, p, c, stream_ptr(out))
+    return (tmp if gy is None else nhwc(gy) + tmp), g_post
+
+
+def _post_act_backward(gym, out, post, d, bias, alpha, gain, n, p, c):
+    """Activation backward of a layer whose ONLY used output is out*post (the next layer's pre-modulated input), in
+    the one pass modconv_act_backward always was:  with the kernel's scale operand set to post*d,
+        g1d = gym * mask * gain * post * d          (gradient w.r.t. the un-demodulated conv / blur output)
+        gsum' = sum_p gym*mask*gain,  dotz' = sum_p gym*mask*gain*z = sum_p gym*out
+    so g_post = dotz' (the next layer's style gradient, formerly its own channel_dot pass over (x, dxm)),
+    gsum = post*gsum', dotz = post*dotz' (bias and demodulation gradients of this layer)."""
+    gym = nhwc(gym)
+    eff = post if d is None else (post * d).contiguous()
+    g1d = torch.empty_like(out)
+    gsum = torch.zeros((n, c), device=out.device, dtype=out.dtype)
+    dotz = torch.zeros_like(gsum)
+    _lib.call("ideas_modconv_act_backward", ptr(g1d), ptr(gsum), ptr(dotz), ptr(gym), ptr(out), ptr(eff), float(alpha),
+              float(gain), n, p, c, stream_ptr(out))
+    return g1d, post * gsum, post * dotz, dotz
 
 
 class ModConv(Function):
@@ -397,52 +430,85 @@ class ModConv(Function):
 
     Restates ModulatedConv2d.forward's non-resampling branch + FusedLeakyReLU
     (stylegan2/model.py:236-248,271-275,375).  ``d`` may be None (demodulate=False) and
-    ``bias`` None with ``act=False`` (plain modulated conv, e.g. ToRGB)."""
+    ``bias`` None with ``act=False`` (plain modulated conv, e.g. ToRGB).
+
+    ``premod``: ``x`` is already s*x -- the producing layer wrote it (see ``post``) -- so no modulation pass runs
+    here, and the gradient returned for ``x`` is the raw data gradient (``s`` gets none from this node).
+    ``post`` (N, K): additionally returns out * post[n,k], the NEXT layer's pre-modulated input; the style gradient
+    of that layer comes back as this node's gradient for ``post``."""
 
     @staticmethod
-    def forward(ctx, x, s, d, wp, bias, g: Geom, act, alpha, gain):
-        require_cuda(x, s, d, wp, bias)
+    def forward(ctx, x, s, d, wp, bias, g: Geom, act, alpha, gain, premod=False, post=None):
+        require_cuda(x, s, d, wp, bias, post)
         x = nhwc(x)
-        s = s.contiguous()
+        s = s.contiguous() if s is not None else None
         d = d.contiguous() if d is not None else None
         _check(x, (g.N, g.C, g.H, g.W), "modconv input")
+        if post is not None and not act:
+            raise RuntimeError("modconv: post-modulation needs the fused activation")
         xm = None
         code = _lib.ACT_LRELU if act else _lib.ACT_NONE
-        if _umma_shape_ok(g) and DEFAULT_IMPL != _lib.IMPL_SIMT:
-            xm = torch.empty_like(x)
-            _lib.call("ideas_scale_channels", ptr(xm), ptr(x), ptr(s), g.N, g.H * g.W, g.C, stream_ptr(x))
+        if premod:
+            xm = x
+            out = _fwd(xm, wp, g, out_scale=d, bias=bias, act=code, alpha=alpha, gain=gain)
+        elif _umma_shape_ok(g) and DEFAULT_IMPL != _lib.IMPL_SIMT:
+            xm = _scale_channels(x, s, g.N, g.H * g.W, g.C)
             out = _fwd(xm, wp, g, out_scale=d, bias=bias, act=code, alpha=alpha, gain=gain)
         else:
             out = _fwd(x, wp, g, in_scale=s, out_scale=d, bias=bias, act=code, alpha=alpha, gain=gain,
                        impl=_lib.IMPL_SIMT)
-        ctx.g, ctx.act, ctx.alpha, ctx.gain = g, act, alpha, gain
+        ctx.g, ctx.act, ctx.alpha, ctx.gain, ctx.premod = g, act, alpha, gain, bool(premod)
+        ctx.set_materialize_grads(False)
+        post = post.contiguous() if post is not None else None
         # the bias is a leaf parameter: save a private copy, never the leaf (train.py:209-216 steps the
         # optimiser between two backwards over this graph)
-        ctx.save_for_backward(x, s, d, wp, bias.clone() if bias is not None else None, out, xm)
-        return out
+        ctx.save_for_backward(None if premod else x, s, d, wp, bias.clone() if bias is not None else None, out, xm, post)
+        if post is None:
+            return out
+        return out, _scale_channels(out, post, g.N, g.OH * g.OW, g.K)
 
     @staticmethod
-    def backward(ctx, gy):
-        x, s, d, wp, bias, out, xm = ctx.saved_tensors
+    def backward(ctx, gy, gym=None):
+        x, s, d, wp, bias, out, xm, post = ctx.saved_tensors
         g = ctx.g
+        if gy is None and gym is None:
+            return (None,) * 11
         if torch.is_grad_enabled():
             # create_graph=True: differentiate a recomputed composite instead of the fused kernels.  The bias leaf
             # was saved as a detached copy (train.py:209-216), so second-order terms do not reach it; none exist
             # (the output is piecewise linear in the bias).
-            act, alpha, gain = ctx.act, ctx.alpha, ctx.gain
-            gx, gs, gd, gw, _ = _grad_of_composite(
-                lambda x_, s_, d_, w_, b_: _modconv_composite(x_, s_, d_, w_, b_, g, act, alpha, gain),
-                [x, s, d, wp, bias], list(ctx.needs_input_grad[:4]) + [False], gy)
+            act, alpha, gain, premod = ctx.act, ctx.alpha, ctx.gain, ctx.premod
+
+            def fn(x_, s_, d_, w_, b_, p_):
+                o = _modconv_composite(x_, None if premod else s_, d_, w_, b_, g, act, alpha, gain)
+                return o if p_ is None else (o, o * p_.view(g.N, g.K, 1, 1))
+
+            xin = xm if premod else x
+            needs = [ctx.needs_input_grad[0], ctx.needs_input_grad[1] and not premod, ctx.needs_input_grad[2],
+                     ctx.needs_input_grad[3], False, ctx.needs_input_grad[10]]
+            gys = gy if post is None else (gy if gy is not None else torch.zeros_like(out),
+                                           gym if gym is not None else torch.zeros_like(out))
+            gx, gs, gd, gw, _, gp = _grad_of_composite(fn, [xin, s, d, wp, bias, post], needs, gys)
             gb = None
             if bias is not None and ctx.needs_input_grad[4]:
+                gtot = gys if post is None else gys[0] + gys[1] * post.view(g.N, g.K, 1, 1)
                 mask = torch.where(out > 0, 1.0, alpha) * gain if act else 1.0
-                gb = (gy * mask).sum(dim=(0, 2, 3))
-            return gx, gs, gd, gw, gb, None, None, None, None
-        gy = nhwc(gy)
-        st = stream_ptr(gy)
+                gb = (gtot * mask).sum(dim=(0, 2, 3))
+            return gx, gs, gd, gw, gb, None, None, None, None, None, gp
+        st = stream_ptr(out)
         P = g.OH * g.OW
-        gb = gd = None
-        if ctx.act:
+        gb = gd = g_post = None
+        fast_post = post is not None and gy is None
+        if post is not None and not fast_post:
+            gy, g_post = _post_general(gy, gym, out, post, g.N, P, g.K)
+        if fast_post:
+            g1d, gsum, dotz, g_post = _post_act_backward(gym, out, post, d, bias, ctx.alpha, ctx.gain, g.N, P, g.K)
+            if bias is not None:
+                gb = gsum.sum(0)
+            if d is not None:
+                gd = (dotz - (bias * gsum if bias is not None else 0.0)) / d
+        elif ctx.act:
+            gy = nhwc(gy)
             g1d = torch.empty_like(out)
             gsum = torch.zeros((g.N, g.K), device=gy.device, dtype=gy.dtype)
             dotz = torch.zeros_like(gsum)
@@ -453,6 +519,7 @@ class ModConv(Function):
             if d is not None:
                 gd = (dotz - (bias * gsum if bias is not None else 0.0)) / d
         else:
+            gy = nhwc(gy)
             if d is not None:
                 # out = d*u (+bias): dL/dd = sum_p gy*u = sum_p gy*(out-bias)/d ; g1d = gy*d
                 g1d = torch.empty_like(out)
@@ -467,82 +534,123 @@ class ModConv(Function):
                 if bias is not None:
                     gb = gy.sum(dim=(0, 2, 3))
         gx = gs = gw = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[0] or (ctx.needs_input_grad[1] and not ctx.premod):
             dxm = _dgrad(g1d, wp, g)
-            gx = torch.empty_like(x)
-            gs = torch.zeros((g.N, g.C), device=gy.device, dtype=gy.dtype)
-            _lib.call("ideas_channel_dot", ptr(gs), ptr(gx), ptr(x), ptr(dxm), ptr(s), g.N, g.H * g.W, g.C, st)
+            if ctx.premod:
+                gx = dxm                       # the producer turns it into its own gradient and the style gradient
+            else:
+                gx = torch.empty_like(x)
+                gs = torch.zeros((g.N, g.C), device=out.device, dtype=out.dtype)
+                _lib.call("ideas_channel_dot", ptr(gs), ptr(gx), ptr(x), ptr(dxm), ptr(s), g.N, g.H * g.W, g.C, st)
         if ctx.needs_input_grad[3]:
             gw = _wgrad(xm, g1d, g) if xm is not None else _wgrad(x, g1d, g, in_scale=s, impl=_lib.IMPL_SIMT)
-        return gx, gs, gd, gw, gb, None, None, None, None
+        return gx, gs, gd, gw, gb, None, None, None, None, None, g_post
 
 
 class ModConvUp(Function):
     """out = gain * lrelu(blur(d * conv_transpose(s * x, w, stride 2)) + bias)  -- the upsampling
     branch of ModulatedConv2d + its Blur + FusedLeakyReLU (stylegan2/model.py:250-261,375).
     ``wp`` is (taps, Cin, Cout): the packed weight of the stride-2 conv this is the adjoint of.
-    ``g`` is that conv's geometry (x here plays its output-gradient)."""
+    ``g`` is that conv's geometry (x here plays its output-gradient).
+    ``post`` (N, Cout): additionally returns out * post, the next layer's pre-modulated input (see ModConv)."""
 
     @staticmethod
-    def forward(ctx, x, s, d, wp, blur_kernel, blur_pad, bias, g: Geom, act, alpha, gain):
-        require_cuda(x, s, d, wp, blur_kernel, bias)
+    def forward(ctx, x, s, d, wp, blur_kernel, blur_pad, bias, g: Geom, act, alpha, gain, post=None):
+        require_cuda(x, s, d, wp, blur_kernel, bias, post)
         if act and bias is None:
             raise RuntimeError("modconv-up: the fused activation needs a bias")
+        if post is not None and not act:
+            raise RuntimeError("modconv-up: post-modulation needs the fused activation")
         x = nhwc(x)
         s = s.contiguous()
         d = d.contiguous() if d is not None else None
         _check(x, (g.N, g.K, g.OH, g.OW), "modconv-up input")
         xm = None
         if _umma_shape_ok(g) and DEFAULT_IMPL != _lib.IMPL_SIMT:
-            xm = torch.empty_like(x)
-            _lib.call("ideas_scale_channels", ptr(xm), ptr(x), ptr(s), g.N, g.OH * g.OW, g.K, stream_ptr(x))
+            xm = _scale_channels(x, s, g.N, g.OH * g.OW, g.K)
             u = _dgrad(xm, wp, g, in_scale=d)
         else:
             u = _dgrad(x, wp, g, in_scale=d, out_scale=s, impl=_lib.IMPL_SIMT)
         kernel = blur_kernel.contiguous()
         out = _upfirdn_run(u, kernel, (1, 1), (1, 1), blur_pad, bias=bias if act else None, alpha=alpha, gain=gain)
         ctx.g, ctx.act, ctx.alpha, ctx.gain, ctx.blur_pad = g, act, alpha, gain, blur_pad
+        ctx.set_materialize_grads(False)
+        post = post.contiguous() if post is not None else None
         ctx.save_for_backward(x, s, d, wp, kernel, u, out if act else None, xm,
-                              bias.clone() if (act and bias is not None) else None)
-        return out
+                              bias.clone() if (act and bias is not None) else None, post)
+        if post is None:
+            return out
+        return out, _scale_channels(out, post, g.N, out.shape[2] * out.shape[3], g.C)
 
     @staticmethod
-    def backward(ctx, gy):
-        x, s, d, wp, kernel, u, out, xm, bias_copy = ctx.saved_tensors
+    def backward(ctx, gy, gym=None):
+        x, s, d, wp, kernel, u, out, xm, bias_copy, post = ctx.saved_tensors
         g = ctx.g
+        if gy is None and gym is None:
+            return (None,) * 12
         if torch.is_grad_enabled():
             act, alpha, gain, blur_pad = ctx.act, ctx.alpha, ctx.gain, ctx.blur_pad
-            gx, gs, gd, gw, _ = _grad_of_composite(
-                lambda x_, s_, d_, w_, b_: _modconv_up_composite(x_, s_, d_, w_, kernel, blur_pad, b_, g, act, alpha, gain),
-                [x, s, d, wp, bias_copy], list(ctx.needs_input_grad[:4]) + [False], gy)
+
+            def fn(x_, s_, d_, w_, b_, p_):
+                o = _modconv_up_composite(x_, s_, d_, w_, kernel, blur_pad, b_, g, act, alpha, gain)
+                return o if p_ is None else (o, o * p_.view(g.N, g.C, 1, 1))
+
+            gys = gy if post is None else (gy if gy is not None else torch.zeros_like(out),
+                                           gym if gym is not None else torch.zeros_like(out))
+            gx, gs, gd, gw, _, gp = _grad_of_composite(fn, [x, s, d, wp, bias_copy, post],
+                                                       list(ctx.needs_input_grad[:4]) + [False, ctx.needs_input_grad[11]], gys)
             gb = None
             if act and ctx.needs_input_grad[6]:
-                gb = (gy * torch.where(out > 0, 1.0, alpha) * gain).sum(dim=(0, 2, 3))
-            return gx, gs, gd, gw, None, None, gb, None, None, None, None
-        gy = nhwc(gy)
-        st = stream_ptr(gy)
-        gb = None
-        if ctx.act:
-            g1, gb = FusedLeakyReLUFunctionBackward.apply(gy, out, ctx.needs_input_grad[6], ctx.alpha, ctx.gain)
+                gtot = gys if post is None else gys[0] + gys[1] * post.view(g.N, g.C, 1, 1)
+                gb = (gtot * torch.where(out > 0, 1.0, alpha) * gain).sum(dim=(0, 2, 3))
+            return gx, gs, gd, gw, None, None, gb, None, None, None, None, gp
+        ref = out if out is not None else u
+        st = stream_ptr(ref)
+        P_out = ref.shape[2] * ref.shape[3]
+        gb = g_post = None
+        if post is not None and gy is None:
+            # the only consumer is the next layer's pre-modulated input: activation backward, the factor post[n,c] and
+            # that layer's style gradient in one pass (see _post_act_backward)
+            g1, gsum, _, g_post = _post_act_backward(gym, out, post, None, None, ctx.alpha, ctx.gain, g.N, P_out, g.C)
+            if ctx.needs_input_grad[6]:
+                gb = gsum.sum(0)
         else:
-            g1 = gy
-        g_pad = _grad_pad((u.shape[2], u.shape[3]), (gy.shape[2], gy.shape[3]), kernel.shape, (1, 1), (1, 1),
+            if post is not None:
+                gy, g_post = _post_general(gy, gym, out, post, g.N, P_out, g.C)
+            gy = nhwc(gy)
+            if ctx.act:
+                g1, gb = FusedLeakyReLUFunctionBackward.apply(gy, out, ctx.needs_input_grad[6], ctx.alpha, ctx.gain)
+            else:
+                g1 = gy
+        g_pad = _grad_pad((u.shape[2], u.shape[3]), (g1.shape[2], g1.shape[3]), kernel.shape, (1, 1), (1, 1),
                           ctx.blur_pad)
-        gu = _upfirdn_run(g1, torch.flip(kernel, [0, 1]), (1, 1), (1, 1), g_pad)
+        gkernel = torch.flip(kernel, [0, 1])
         gd = None
-        if d is not None:
-            gud = torch.empty_like(gu)
-            dot = torch.zeros((g.N, g.C), device=gy.device, dtype=gy.dtype)
-            _lib.call("ideas_channel_dot", ptr(dot), ptr(gud), ptr(u), ptr(gu), ptr(d), g.N, g.H * g.W, g.C, st)
+        if d is not None and _blur_act_bwd_ok(g.C) and kernel.shape[0] <= 4 and kernel.shape[1] <= 4 and g.N <= 65535:
+            # blur^T, the demodulation scale and dL/dd = sum_p gu * u / d in ONE kernel: the blurred gradient is
+            # never written (was: blur backward, then a channel_dot pass over (u, gu))
+            g1 = nhwc(g1)
+            gud = torch.empty_like(u)
+            dot = torch.zeros((g.N, g.C), device=u.device, dtype=u.dtype)
+            _lib.call("ideas_blur_scale_dot_backward", ptr(gud), ptr(dot), ptr(g1), ptr(u), ptr(d), ptr(gkernel), g.N,
+                      g1.shape[2], g1.shape[3], g.C, gkernel.shape[0], gkernel.shape[1], g_pad[0], g_pad[1], g_pad[2],
+                      g_pad[3], st)
             gd = dot / d
         else:
-            gud = gu
+            gu = _upfirdn_run(g1, gkernel, (1, 1), (1, 1), g_pad)
+            if d is not None:
+                gud = torch.empty_like(gu)
+                dot = torch.zeros((g.N, g.C), device=u.device, dtype=u.dtype)
+                _lib.call("ideas_channel_dot", ptr(dot), ptr(gud), ptr(u), ptr(gu), ptr(d), g.N, g.H * g.W, g.C, st)
+                gd = dot / d
+            else:
+                gud = gu
         gx = gs = gw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             dxm = _fwd(gud, wp, g)                                  # adjoint of the transposed conv
             gx = torch.empty_like(x)
-            gs = torch.zeros((g.N, g.K), device=gy.device, dtype=gy.dtype)
+            gs = torch.zeros((g.N, g.K), device=u.device, dtype=u.dtype)
             _lib.call("ideas_channel_dot", ptr(gs), ptr(gx), ptr(x), ptr(dxm), ptr(s), g.N, g.OH * g.OW, g.K, st)
         if ctx.needs_input_grad[3]:
             gw = _wgrad(gud, xm, g) if xm is not None else _wgrad(gud, x, g, out_scale=s, impl=_lib.IMPL_SIMT)
-        return gx, gs, gd, gw, None, None, (gb if (ctx.act and ctx.needs_input_grad[6]) else None), None, None, None, None
+        return gx, gs, gd, gw, None, None, (gb if (ctx.act and ctx.needs_input_grad[6]) else None), None, None, None, None, g_post

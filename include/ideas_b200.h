@@ -131,6 +131,15 @@ int ideas_blur_act_backward(float* gx, float* gbias, const float* g, const float
                             int major, int in_h, int in_w, int minor, int kernel_h, int kernel_w,
                             int pad_x0, int pad_x1, int pad_y0, int pad_y1, float alpha, float gain, void* stream);
 
+/* Backward of  u -> d[n,c]*u -> Blur  (up-sampling ModulatedConv2d, stylegan2/model.py:250-261) in one pass:
+ * v = upfirdn2d(g, kernel [already flipped], gradient pads); gx = v * scale[n,c] (scale may be NULL);
+ * dot[n,c] += sum over pixels of v * ref (ref has gx's shape; dot (major x minor) zero-initialised by the caller).
+ * Fast path only (<= 4x4 kernel, channels % 4 == 0, power-of-two channel count): IDEAS_ERR_UNSUPPORTED otherwise. */
+int ideas_blur_scale_dot_backward(float* gx, float* dot, const float* g, const float* ref, const float* scale,
+                                  const float* kernel, int major, int in_h, int in_w, int minor,
+                                  int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                                  void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A1/A5  convolutions (new native unit; the reference calls cuDNN here)
  *

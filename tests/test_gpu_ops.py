@@ -559,3 +559,37 @@ def test_conv2d_residual_merge_autograd(conv_mode):
     assert T.rel(y1, y0) <= tol
     for a, c in zip(g1, g0):
         assert T.rel(a, c) <= tol * 5
+
+
+@pytest.mark.parametrize("up", [False, True])
+def test_styled_conv_pair_with_premodulation(conv_mode, up):
+    """conv1 -> conv2 of a StyledResBlock with conv2's style folded into conv1's output (post / premodulated path of
+    op/conv.py) against the plain composition of the two modules: output and every gradient, incl. both styles."""
+    from ideas_b200.stylegan2 import model as M
+    torch.manual_seed(11)
+    c1 = M.StyledConv_without_noise(64, 64, 3, 24, upsample=up).cuda()
+    c2 = M.StyledConv_without_noise(64, 96, 3, 24).cuda()
+    for c in (c1, c2):
+        c.activate.bias.data.normal_()
+    x = torch.randn(2, 64, 12, 12).cuda().requires_grad_(True)
+    st = (torch.rand(2, 24) * 2 - 1).cuda().requires_grad_(True)
+    params = [x, st] + list(c1.parameters()) + list(c2.parameters())
+    plain = c2(c1(x, st), st)
+    gy = torch.randn_like(plain)
+    want = torch.autograd.grad(plain, params, gy)
+    s2 = c2.conv.modulation(st)
+    a, am = c1(x, st, post_modulation=s2)
+    fused = c2(am, st, modulation=s2, premodulated=True)
+    got = torch.autograd.grad(fused, params, gy)
+    tol = 2e-5 if conv_mode == "fp32" else 1e-3
+    assert T.rel(fused, plain) <= tol
+    assert T.rel(a, c1(x, st)) <= tol
+    for g_, w_, p_ in zip(got, want, params):
+        # same kernels and same mask (both sides run the same forward), so no flip noise: plain relative error
+        assert T.rel(g_, w_) <= 5 * tol, tuple(p_.shape)
+    # both outputs of conv1 used: the general path
+    a, am = c1(x, st, post_modulation=s2)
+    both = torch.autograd.grad((c2(am, st, modulation=s2, premodulated=True) * gy).sum() + (a * a).sum(), params)
+    ref = torch.autograd.grad((c2(c1(x, st), st) * gy).sum() + (c1(x, st) ** 2).sum(), params)
+    for g_, w_ in zip(both, ref):
+        assert T.rel(g_, w_) <= 5 * tol

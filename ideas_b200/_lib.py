@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "ideas_upfirdn2d_res": [_P, _P, _P] + [c_int] * 14 + [_P, c_float, c_float, _P, c_float, _P],
     "ideas_blur_act_backward": [_P, _P, _P, _P, _P] + [c_int] * 10 + [c_float, c_float, _P],
     "ideas_blur_scale_dot_backward": [_P, _P, _P, _P, _P, _P] + [c_int] * 10 + [_P],
+    "ideas_blur_bias_act_post": [_P, _P, _P, _P, _P, _P] + [c_int] * 10 + [c_float, c_float, _P],
     "ideas_pack_weight": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P],
     "ideas_unpack_weight_grad": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P],
     "ideas_repack_dgrad": [_P, _P, c_int, c_int, c_int, _P],

@@ -32,6 +32,8 @@ struct UpfirdnParams {
   float alpha, gain;
   const float* residual;   // out-shaped; merged as (result + residual) * res_scale (up2 fast path only)
   float res_scale;
+  float* out2;             // EPI 1 only: second output out2 = out * post[n,c] (the next layer's pre-modulated input)
+  const float* post;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -188,6 +190,11 @@ __device__ __forceinline__ void blur4_general(float* __restrict__ out, const flo
         if (EPI >= 2) rv = ld_stream4(refp + (int64_t)oy * orow + (int64_t)j * p.minor);
         blur_epilogue<EPI>(done, b4, p, rv, bsum);
         st_stream4(o + (int64_t)oy * orow + (int64_t)j * p.minor, done);
+        if (EPI == 1 && p.out2 != nullptr) {
+          const float4 q = *reinterpret_cast<const float4*>(p.post + (int64_t)m * p.minor + c);
+          st_stream4(p.out2 + (o - out) + (int64_t)oy * orow + (int64_t)j * p.minor,
+                     make_float4(done.x * q.x, done.y * q.y, done.z * q.z, done.w * q.w));
+        }
       }
     }
   }
@@ -233,7 +240,8 @@ template <int XT, int EPI, bool INTERIOR>
 __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const float* __restrict__ xin, const UpfirdnParams& p,
                                                const unsigned long long (&kx)[4], const unsigned long long (&ky)[4],
                                                int ox0, int ix0, int oy0, int oy1, const float4& b4,
-                                               const float* __restrict__ refp, float4& bsum) {
+                                               const float* __restrict__ refp, float4& bsum,
+                                               float* __restrict__ o2 = nullptr, const float4& post4 = float4{1.f, 1.f, 1.f, 1.f}) {
   const int64_t orow = (int64_t)p.out_w * p.minor;
   const int64_t irow = (int64_t)p.in_w * p.minor;
   bool colok[XT + 3];
@@ -283,6 +291,9 @@ __device__ __forceinline__ void blur4sep_strip(float* __restrict__ o, const floa
             unpack2(dh, done.z, done.w);
             blur_epilogue<EPI>(done, b4, p, refv[j], bsum);
             st_stream4(op + (int64_t)j * p.minor, done);
+            if (EPI == 1 && o2 != nullptr)
+              st_stream4(o2 + (op - o) + (int64_t)j * p.minor,
+                         make_float4(done.x * post4.x, done.y * post4.y, done.z * post4.z, done.w * post4.w));
           }
         }
         rp += irow;
@@ -343,8 +354,11 @@ __global__ void __launch_bounds__(128) blur4_nhwc_kernel(float* __restrict__ out
     if (EPI == 3) b4 = bias ? *reinterpret_cast<const float4*>(bias + (int64_t)m * p.minor + c) : make_float4(1.f, 1.f, 1.f, 1.f);
     const bool interior = ix0 >= 0 && ix0 + XT + 3 <= p.in_w && ox0 + XT <= p.out_w && oy0 - p.pad_y0 >= 0 &&
                           oy1 - 1 - p.pad_y0 + 3 < p.in_h;
-    if (interior) blur4sep_strip<XT, EPI, true>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum);
-    else blur4sep_strip<XT, EPI, false>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum);
+    float* o2 = (EPI == 1 && p.out2) ? p.out2 + obase : nullptr;
+    float4 post4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (o2) post4 = *reinterpret_cast<const float4*>(p.post + (int64_t)m * p.minor + c);
+    if (interior) blur4sep_strip<XT, EPI, true>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum, o2, post4);
+    else blur4sep_strip<XT, EPI, false>(o, xin, p, kx, ky, ox0, ix0, oy0, oy1, b4, refp, bsum, o2, post4);
   }
   if (EPI >= 2 && gbias != nullptr) {
     if (EPI == 3) gbias += (int64_t)blockIdx.z * p.minor;      // per-(image, channel) sums
@@ -642,6 +656,7 @@ extern "C" int ideas_upfirdn2d_res(float* out, const float* x, const float* kern
   p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kernel_w + down_x) / down_x;
   p.alpha = alpha; p.gain = gain;
   p.residual = residual; p.res_scale = res_scale;
+  p.out2 = nullptr; p.post = nullptr;
   const bool empty = major == 0 || in_h == 0 || in_w == 0;
   IDEAS_REQUIRE(empty || ((in_h * up_y + pad_y0 + pad_y1 - kernel_h) >= 0 && (in_w * up_x + pad_x0 + pad_x1 - kernel_w) >= 0),
                 "upfirdn2d: padding/cropping leaves no output (in %dx%d, kernel %dx%d)", in_h, in_w, kernel_h, kernel_w);
@@ -725,6 +740,7 @@ extern "C" int ideas_blur_act_backward(float* gx, float* gbias, const float* g, 
   p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
   p.alpha = alpha; p.gain = gain;
   p.residual = nullptr; p.res_scale = 1.f;
+  p.out2 = nullptr; p.post = nullptr;
   IDEAS_REQUIRE(p.out_h >= 1 && p.out_w >= 1, "blur_act_backward: padding/cropping leaves no output");
   if (major == 0) return IDEAS_OK;
   IDEAS_REQUIRE(gx && g && ref && kernel, "blur_act_backward: null pointer");
@@ -762,6 +778,7 @@ extern "C" int ideas_blur_scale_dot_backward(float* gx, float* dot, const float*
   p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
   p.alpha = alpha; p.gain = gain;
   p.residual = nullptr; p.res_scale = 1.f;
+  p.out2 = nullptr; p.post = nullptr;
   IDEAS_REQUIRE(p.out_h >= 1 && p.out_w >= 1, "blur_scale_dot_backward: padding/cropping leaves no output");
   if (major == 0) return IDEAS_OK;
   IDEAS_REQUIRE(gx && g && ref && kernel, "blur_scale_dot_backward: null pointer");
@@ -776,5 +793,39 @@ extern "C" int ideas_blur_scale_dot_backward(float* gx, float* dot, const float*
   dim3 grid(ceil_div(ceil_div(p.out_w, XT) * c4n, 128), ceil_div(p.out_h, ROWS), major);
   blur4_nhwc_kernel<ROWS, XT, 3><<<grid, 128, 0, st>>>(gx, g, kernel, scale, p, ref, dot);
   IDEAS_CHECK_LAUNCH("blur_scale_dot_backward");
+  return IDEAS_OK;
+}
+
+// Blur -> FusedLeakyReLU of an up-sampling StyledConv (stylegan2/model.py:261,375) with a second output for the NEXT
+// layer: out = gain * lrelu(blur(x) + bias[c]),  out2 = out * post[n,c]  (that layer's style modulation, so it needs
+// no modulation pass of its own).  up = down = 1 fast path only (<= 4x4 kernel, channels % 4 == 0).
+extern "C" int ideas_blur_bias_act_post(float* out, float* out2, const float* x, const float* kernel, const float* bias,
+                                        const float* post, int major, int in_h, int in_w, int minor, int kernel_h,
+                                        int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1, float alpha,
+                                        float gain, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IDEAS_REQUIRE(major >= 0 && in_h >= 1 && in_w >= 1 && minor >= 1, "blur_bias_act_post: bad input shape");
+  IDEAS_REQUIRE(kernel_h >= 1 && kernel_w >= 1, "blur_bias_act_post: empty FIR kernel");
+  UpfirdnParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kernel_h; p.kw = kernel_w;
+  p.up_x = p.up_y = p.down_x = p.down_y = 1; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.out_h = in_h + pad_y0 + pad_y1 - kernel_h + 1;
+  p.out_w = in_w + pad_x0 + pad_x1 - kernel_w + 1;
+  p.alpha = alpha; p.gain = gain;
+  p.residual = nullptr; p.res_scale = 1.f;
+  p.out2 = out2; p.post = post;
+  IDEAS_REQUIRE(p.out_h >= 1 && p.out_w >= 1, "blur_bias_act_post: padding/cropping leaves no output");
+  if (major == 0) return IDEAS_OK;
+  IDEAS_REQUIRE(out && out2 && x && kernel && bias && post, "blur_bias_act_post: null pointer");
+  const bool fast = kernel_h <= 4 && kernel_w <= 4 && minor % 4 == 0 && aligned16(out) && aligned16(out2) && aligned16(x) &&
+                    aligned16(bias) && aligned16(post) && major <= 65535;
+  if (!fast) {
+    set_error("blur_bias_act_post: needs a <= 4x4 kernel and channels %% 4 == 0 (C=%d)", minor);
+    return IDEAS_ERR_UNSUPPORTED;
+  }
+  constexpr int ROWS = 32, XT = 2;
+  dim3 grid(ceil_div(ceil_div(p.out_w, XT) * (minor / 4), 128), ceil_div(p.out_h, ROWS), major);
+  blur4_nhwc_kernel<ROWS, XT, 1><<<grid, 128, 0, st>>>(out, x, kernel, bias, p, nullptr, nullptr);
+  IDEAS_CHECK_LAUNCH("blur_bias_act_post");
   return IDEAS_OK;
 }

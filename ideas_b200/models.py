@@ -28,6 +28,7 @@ from .stylegan2.op.linear import matmul_nt
 from .stylegan2.op.elementwise import add_scale, reflect_pad
 
 _INV_SQRT2 = 1.0 / math.sqrt(2.0)
+_AB_NO_PREMOD = __import__("os").environ.get("IDEAS_AB_NO_PREMOD", "0") == "1"      # measurement-only A/B switch
 
 
 class EqualConvTranspose2d(nn.Module):
@@ -178,7 +179,7 @@ class StyledResBlock(nn.Module):
     def forward(self, input, style, noise=None, modulation=None):
         """``modulation``: optional (s1, s2), the outputs of conv1 / conv2's modulation linears."""
         m1, m2 = modulation if modulation is not None else (None, None)
-        if input.is_cuda:
+        if input.is_cuda and not _AB_NO_PREMOD:
             # conv1 hands conv2 its input already multiplied by conv2's style (s2 * a): conv2 runs no modulation
             # pass, and its style gradient comes out of conv1's activation backward for free (op/conv.py, ``post``)
             if m2 is None:

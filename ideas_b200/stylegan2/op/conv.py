@@ -572,15 +572,29 @@ class ModConvUp(Function):
         else:
             u = _dgrad(x, wp, g, in_scale=d, out_scale=s, impl=_lib.IMPL_SIMT)
         kernel = blur_kernel.contiguous()
-        out = _upfirdn_run(u, kernel, (1, 1), (1, 1), blur_pad, bias=bias if act else None, alpha=alpha, gain=gain)
+        post = post.contiguous() if post is not None else None
+        out_mod = None
+        if post is not None and kernel.shape[0] <= 4 and kernel.shape[1] <= 4 and g.C % 4 == 0 and g.N <= 65535:
+            # Blur + bias + leaky ReLU writing BOTH the activation and its post-modulated copy (one kernel)
+            kh, kw = kernel.shape
+            oh = u.shape[2] + blur_pad[2] + blur_pad[3] - kh + 1
+            ow = u.shape[3] + blur_pad[0] + blur_pad[1] - kw + 1
+            out = empty_nhwc(g.N, g.C, oh, ow, u)
+            out_mod = torch.empty_like(out)
+            _lib.call("ideas_blur_bias_act_post", ptr(out), ptr(out_mod), ptr(u), ptr(kernel), ptr(bias), ptr(post), g.N,
+                      u.shape[2], u.shape[3], g.C, kh, kw, blur_pad[0], blur_pad[1], blur_pad[2], blur_pad[3],
+                      float(alpha), float(gain), stream_ptr(u))
+        else:
+            out = _upfirdn_run(u, kernel, (1, 1), (1, 1), blur_pad, bias=bias if act else None, alpha=alpha, gain=gain)
         ctx.g, ctx.act, ctx.alpha, ctx.gain, ctx.blur_pad = g, act, alpha, gain, blur_pad
         ctx.set_materialize_grads(False)
-        post = post.contiguous() if post is not None else None
         ctx.save_for_backward(x, s, d, wp, kernel, u, out if act else None, xm,
                               bias.clone() if (act and bias is not None) else None, post)
         if post is None:
             return out
-        return out, _scale_channels(out, post, g.N, out.shape[2] * out.shape[3], g.C)
+        if out_mod is None:
+            out_mod = _scale_channels(out, post, g.N, out.shape[2] * out.shape[3], g.C)
+        return out, out_mod
 
     @staticmethod
     def backward(ctx, gy, gym=None):

@@ -140,6 +140,14 @@ int ideas_blur_scale_dot_backward(float* gx, float* dot, const float* g, const f
                                   int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                                   void* stream);
 
+/* Blur -> FusedLeakyReLU (stylegan2/model.py:261,375) with a second output for the next layer:
+ * out = gain*lrelu(upfirdn2d(x, kernel, pads) + bias[c]); out2 = out * post[n,c] (post: major x minor).
+ * up = down = 1 fast path only; IDEAS_ERR_UNSUPPORTED otherwise. */
+int ideas_blur_bias_act_post(float* out, float* out2, const float* x, const float* kernel, const float* bias,
+                             const float* post, int major, int in_h, int in_w, int minor,
+                             int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                             float alpha, float gain, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * A1/A5  convolutions (new native unit; the reference calls cuDNN here)
  *

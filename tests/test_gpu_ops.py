@@ -588,6 +588,7 @@ def test_styled_conv_pair_with_premodulation(conv_mode, up):
         # same kernels and same mask (both sides run the same forward), so no flip noise: plain relative error
         assert T.rel(g_, w_) <= 5 * tol, tuple(p_.shape)
     # both outputs of conv1 used: the general path
+    s2 = c2.conv.modulation(st)
     a, am = c1(x, st, post_modulation=s2)
     both = torch.autograd.grad((c2(am, st, modulation=s2, premodulated=True) * gy).sum() + (a * a).sum(), params)
     ref = torch.autograd.grad((c2(c1(x, st), st) * gy).sum() + (c1(x, st) ** 2).sum(), params)

@@ -716,6 +716,7 @@ constexpr int kPmhEpiWarps = 8;
 constexpr uint32_t kPmhSmemBudget = 224 * 1024;
 
 std::atomic<int> g_pmh_mode{1};               // 0 = never, 1 = heuristic, 2 = whenever eligible
+std::atomic<int> g_pmh_resident{1};           // keep small filters in shared memory for the CTA's lifetime
 std::atomic<int> g_pmh_xstages{2};            // slab ring depth (2 or 3)
 std::atomic<int> g_pmh_minbw{0};              // tile search: smallest tile width considered (0 = no bound)
 
@@ -736,6 +737,7 @@ struct alignas(64) PmhParams {
   int tiles_x, tiles_y, ktiles, items;
   int ntaps, csteps;
   int x_stages, w_stages;
+  int w_resident;   // all ntaps*csteps weight tiles stay in shared memory for the CTA's lifetime (one k-tile, <= 80 KB)
   uint32_t x_slot_bytes, x_tx_bytes, w_bytes;
   int act;
   float alpha, gain;
@@ -793,18 +795,28 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
     if (lane == 0) {
       // ===== weight tiles: one (32-channel step, tap) per ring slot, OCT rows of 128 B =====
       ptx::tma_prefetch_desc(&p.w);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const int k0 = (item % p.ktiles) * p.oct;
+      if (p.w_resident) {
+        // the whole filter fits: fetch it once, every item reuses it (32 -> 64 / 64 -> 32 channel layers, where an
+        // item's weight tiles would otherwise cost as much L2 traffic as its activations)
+        const uint32_t fb = ptx::smem_u32(&wfull[0]);
+        ptx::mbar_arrive_expect_tx(fb, (uint32_t)(p.csteps * p.ntaps) * p.w_bytes);
         for (int cs = 0; cs < p.csteps; ++cs)
-          for (int t = 0; t < p.ntaps; ++t) {
-            ptx::mbar_wait(ptx::smem_u32(&wempty[stage]), phase ^ 1u);
-            const uint32_t fb = ptx::smem_u32(&wfull[stage]);
-            ptx::mbar_arrive_expect_tx(fb, p.w_bytes);
-            ptx::tma_load_3d(wring + stage * p.w_bytes, &p.w, fb, cs * kBlockK, k0, p.taps[t].widx);
-            if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
-          }
+          for (int t = 0; t < p.ntaps; ++t)
+            ptx::tma_load_3d(wring + (uint32_t)(cs * p.ntaps + t) * p.w_bytes, &p.w, fb, cs * kBlockK, 0, p.taps[t].widx);
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+          const int k0 = (item % p.ktiles) * p.oct;
+          for (int cs = 0; cs < p.csteps; ++cs)
+            for (int t = 0; t < p.ntaps; ++t) {
+              ptx::mbar_wait(ptx::smem_u32(&wempty[stage]), phase ^ 1u);
+              const uint32_t fb = ptx::smem_u32(&wfull[stage]);
+              ptx::mbar_arrive_expect_tx(fb, p.w_bytes);
+              ptx::tma_load_3d(wring + stage * p.w_bytes, &p.w, fb, cs * kBlockK, k0, p.taps[t].widx);
+              if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
+            }
+        }
       }
     }
   } else if (warp == 1) {
@@ -829,9 +841,11 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = ptx::idesc_tf32(128, p.oct, 0, 0);
+      const bool resident = p.w_resident != 0;
       int ws = 0, xs = 0;
       uint32_t wphase = 0, xphase = 0;
       int it = 0;
+      if (resident) ptx::mbar_wait(ptx::smem_u32(&wfull[0]), 0);
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int buf = it & 1;
         ptx::mbar_wait(ptx::smem_u32(&tempty[buf]), ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -841,7 +855,8 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
           ptx::mbar_wait(ptx::smem_u32(&xfull[xs]), xphase);
           const uint32_t xa = xring + xs * p.x_slot_bytes;
           for (int t = 0; t < p.ntaps; ++t) {
-            ptx::mbar_wait(ptx::smem_u32(&wfull[ws]), wphase);
+            if (resident) ws = cs * p.ntaps + t;
+            else ptx::mbar_wait(ptx::smem_u32(&wfull[ws]), wphase);
             ptx::tc_fence_after();
             const uint64_t bdesc = ptx::smem_desc_sw128(wring + ws * p.w_bytes, 16, 1024);
             const uint32_t a0 = xa + (uint32_t)p.taps[t].rowoff * 128u;
@@ -851,8 +866,10 @@ __global__ void __launch_bounds__(kPmhThreads, 1) conv_umma_pmh_kernel(const __g
               for (int k = 0; k < kBlockK / kUmmaK; ++k)
                 ptx::mma_tf32(acc + s * p.oct, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cs | t | k) != 0));
             }
-            ptx::mma_commit(ptx::smem_u32(&wempty[ws]));
-            if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
+            if (!resident) {
+              ptx::mma_commit(ptx::smem_u32(&wempty[ws]));
+              if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
+            }
           }
           ptx::mma_commit(ptx::smem_u32(&xempty[xs]));
           if (++xs == p.x_stages) { xs = 0; xphase ^= 1u; }
@@ -961,13 +978,13 @@ struct PmhTile {
 };
 
 // (bw, bh) minimising modelled time per image = tiles * max(MMA cycles, L2-feed cycles) per 32-channel step
-bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile* out) {
+bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, int resident_tiles, PmhTile* out) {
   struct Key { int a, b, c, d, e, f; bool operator<(const Key& o) const { return memcmp(this, &o, sizeof(Key)) < 0; } };
   static std::mutex mu;
   static std::map<Key, PmhTile> cache;
   const int xst = g_pmh_xstages.load() == 3 ? 3 : 2;
   const int minbw = g_pmh_minbw.load();
-  const Key key{QW, QH, hx * 16 + hy, ntaps, oct, xst * 1024 + minbw};
+  const Key key{QW, QH, hx * 16 + hy, ntaps + 64 * resident_tiles, oct, xst * 1024 + minbw};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -985,16 +1002,17 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, PmhTile
       const int nsub = ceil_div(bh * bwp, 128);
       if (nsub > max_sub) break;
       const uint32_t slot = (uint32_t)((nsub * 128 + hy * bwp + hx) * 128 + 1023) & ~1023u;
-      if (xst * slot + 4 * w_bytes + kPmhStageBytes > kPmhSmemBudget) break;
+      const uint32_t wmin = resident_tiles ? (uint32_t)resident_tiles * w_bytes : 4 * w_bytes;
+      if (xst * slot + wmin + kPmhStageBytes > kPmhSmemBudget) break;
       const int tx = ceil_div(QW, bw), ty = ceil_div(QH, bh);
       const double mma = (double)ntaps * nsub * 4 * (oct / 2.0);
-      const double l2 = ((double)ntaps * w_bytes + (double)(bh + hy) * bwp * 128) / 48.0;
+      const double l2 = ((resident_tiles ? 0.0 : (double)ntaps * w_bytes) + (double)(bh + hy) * bwp * 128) / 48.0;
       const double cyc = (double)tx * ty * ((mma > l2 ? mma : l2) + 24.0);
       if (cyc < best.cycles) {
         best.bw = bw; best.bwp = bwp; best.bh = bh; best.nsub = nsub; best.tiles_x = tx; best.tiles_y = ty;
         best.slot_bytes = slot; best.cycles = cyc;
         const int ws = (int)((kPmhSmemBudget - kPmhStageBytes - xst * slot) / w_bytes);
-        best.w_stages = ws > kPmhMaxWStages ? kPmhMaxWStages : ws;
+        best.w_stages = resident_tiles ? resident_tiles : (ws > kPmhMaxWStages ? kPmhMaxWStages : ws);
         best.x_stages = xst;
       }
     }
@@ -1029,8 +1047,12 @@ int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float
     if (oct == 128 && !(residual && g.IC <= 128)) return IDEAS_ERR_UNSUPPORTED;
     if (g.IC > 128) return IDEAS_ERR_UNSUPPORTED;
   }
+  // resident weights: one k-tile and the whole filter within 80 KB (and the ring's 16 barriers)
+  const int wtiles = g.ntaps * (g.IC / kBlockK);
+  const bool resident = g_pmh_resident.load() && g.OC == oct && wtiles <= kPmhMaxWStages &&
+                        (uint32_t)wtiles * (uint32_t)oct * 128u <= 80u * 1024u;
   PmhTile tile;
-  if (!choose_pmh_tile(g.QW, g.QH, hx, hy, g.ntaps, oct, &tile)) return IDEAS_ERR_UNSUPPORTED;
+  if (!choose_pmh_tile(g.QW, g.QH, hx, hy, g.ntaps, oct, resident ? wtiles : 0, &tile)) return IDEAS_ERR_UNSUPPORTED;
 
   PmhParams p;
   p.dst = dst; p.out_scale = out_scale; p.bias = bias; p.residual = residual; p.res_scale = res_scale;
@@ -1047,6 +1069,8 @@ int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float
   p.ntaps = g.ntaps; p.csteps = g.IC / kBlockK;
   p.x_stages = tile.x_stages;
   p.w_stages = tile.w_stages;
+  p.w_resident = resident ? 1 : 0;
+  p.w_resident = resident ? 1 : 0;
   p.x_slot_bytes = tile.slot_bytes;
   p.x_tx_bytes = (uint32_t)(p.box_rows * p.bwp * 128);
   p.w_bytes = (uint32_t)oct * 128u;
@@ -1537,6 +1561,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "pmh")) {
     ideas::g_pmh_mode.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pmh_resident")) {
+    ideas::g_pmh_resident.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "pmh_xstages")) {

@@ -9,14 +9,15 @@ KEYS = [
     ("gpu__time_duration.sum", "duration"),
     ("dram__bytes_read.sum", "dram read"),
     ("dram__bytes_write.sum", "dram write"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
+    ("dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "dram read % of peak"),
+    ("dram__bytes_write.sum.pct_of_peak_sustained_elapsed", "dram write % of peak"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 % of peak"),
-    ("lts__t_bytes.sum", "L2 bytes"),
-    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM % of peak"),
-    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active %"),
-    ("sm__inst_executed_pipe_tmem.sum", "tmem inst"),
-    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
     ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1 % of peak"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM % of peak"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe cycles active %"),
+    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe (realtime) %"),
+    ("smsp__sass_inst_executed_op_tmem_ldt.sum", "tcgen05.ld inst"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("launch__registers_per_thread", "registers/thread"),
     ("launch__grid_size", "grid"),
@@ -46,11 +47,12 @@ for path in args:
     print(f"## {path}\nkernel: {name}")
     got = {}
     for key, label in KEYS:
-        for h, u, v in zip(hdr, units, vals):
-            if h == key or h.endswith("." + key):
-                print(f"  {label:24s} {v} {u}")
-                got[key] = (v, u)
-                break
+        cands = [(h, u, v) for h, u, v in zip(hdr, units, vals) if h == key] or \
+                [(h, u, v) for h, u, v in zip(hdr, units, vals) if h.endswith("." + key) and v.strip()]
+        if cands:
+            h, u, v = cands[0]
+            print(f"  {label:28s} {v} {u}")
+            got[key] = (v, u)
     print()
     if traffic_path and "dram__bytes_read.sum" in got and "dram__bytes_write.sum" in got:
         tot = sum(float(got[k][0].replace(",", "")) * UNIT.get(got[k][1], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))

@@ -1047,10 +1047,9 @@ int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float
     if (oct == 128 && !(residual && g.IC <= 128)) return IDEAS_ERR_UNSUPPORTED;
     if (g.IC > 128) return IDEAS_ERR_UNSUPPORTED;
   }
-  // resident weights: one k-tile and the whole filter within 80 KB (and the ring's 16 barriers)
+  // resident weights: one k-tile and the whole filter within 80 KB (a single barrier covers the one-time load)
   const int wtiles = g.ntaps * (g.IC / kBlockK);
-  const bool resident = g_pmh_resident.load() && g.OC == oct && wtiles <= kPmhMaxWStages &&
-                        (uint32_t)wtiles * (uint32_t)oct * 128u <= 80u * 1024u;
+  const bool resident = g_pmh_resident.load() && g.OC == oct && (uint32_t)wtiles * (uint32_t)oct * 128u <= 80u * 1024u;
   PmhTile tile;
   if (!choose_pmh_tile(g.QW, g.QH, hx, hy, g.ntaps, oct, resident ? wtiles : 0, &tile)) return IDEAS_ERR_UNSUPPORTED;
 

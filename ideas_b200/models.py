@@ -42,6 +42,9 @@ class EqualConvTranspose2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
+    def derived_weights(self):
+        return packed_weight(self.weight, False, self.scale)
+
     def forward(self, input, stride=None):
         cin, cout, k, _ = self.weight.shape
         stride = self.stride if stride is None else stride
@@ -269,17 +272,22 @@ class Generator(nn.Module):
             out = block(out, texture, noise, modulation=mod)
         return self.to_rgb(out)
 
-    def modulations(self, texture):
-        """The 16 modulation linears of one call (stylegan2/model.py:226,239: every ModulatedConv2d maps the SAME
-        texture vector through its own EqualLinear) as ONE GEMM on the row-concatenated weights: s_all =
-        texture @ cat(W_l * scale)^T + cat(bias_l), then split per layer."""
+    def derived_weights(self):
+        """Row-concatenated modulation weights and biases of all layers (cached per training iteration)."""
         lins = [conv.conv.modulation for block in self.layers for conv in (block.conv1, block.conv2)]
 
         def build():
             return (torch.cat([m.effective_weight() for m in lins], 0),
                     torch.cat([m.bias * m.lr_mul for m in lins], 0))
 
-        w_all, b_all = cached(lins[0].weight, "G.modulations", build)
+        return cached(lins[0].weight, "G.modulations", build)
+
+    def modulations(self, texture):
+        """The 16 modulation linears of one call (stylegan2/model.py:226,239: every ModulatedConv2d maps the SAME
+        texture vector through its own EqualLinear) as ONE GEMM on the row-concatenated weights: s_all =
+        texture @ cat(W_l * scale)^T + cat(bias_l), then split per layer."""
+        lins = [conv.conv.modulation for block in self.layers for conv in (block.conv1, block.conv2)]
+        w_all, b_all = self.derived_weights()
         s_all = matmul_nt(texture, w_all) + b_all
         parts = torch.split(s_all, [m.weight.shape[0] for m in lins], dim=1)
         return [(parts[2 * i], parts[2 * i + 1]) for i in range(len(self.layers))]

@@ -95,6 +95,9 @@ class EqualConv2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
+    def derived_weights(self):
+        return packed_weight(self.weight, False, self.scale)
+
     def forward(self, input, activation: FusedLeakyReLU | None = None, stride: int | None = None, residual=None,
                 res_scale: float = 1.0):
         """``activation``: a FusedLeakyReLU module to fuse into the conv epilogue.  ``stride`` overrides the
@@ -136,6 +139,9 @@ class EqualLinear(nn.Module):
         self.activation = activation
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
+
+    def derived_weights(self):
+        return self.effective_weight()
 
     def effective_weight(self):
         """weight * scale as a temporary (shared by the uses of one training iteration): the leaf itself is never
@@ -197,6 +203,17 @@ class ModulatedConv2d(nn.Module):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
                 f"upsample={self.upsample}, downsample={self.downsample})")
 
+    def derived_weights(self):
+        """(packed scaled weight, sum_k (scale*W)^2): functions of the parameter alone, shared by every call of one
+        training iteration (op/conv.py step cache)."""
+        def build():
+            ws = self.weight[0] * self.scale                         # temp, never the leaf (see op/conv.py)
+            wsq = ws.pow(2).sum(dim=(2, 3)) if self.demodulate else None          # (Cout, Cin)
+            # upsampling branch: (taps, Cin, Cout), the packed weight of the stride-2 conv it is the adjoint of
+            return PackWeight.apply(ws, bool(self.upsample), 1.0), wsq
+
+        return cached(self.weight, "modconv", build)
+
     def forward(self, input, style, activation: FusedLeakyReLU | None = None, modulation: torch.Tensor | None = None,
                 premodulated: bool = False, post_modulation: torch.Tensor | None = None):
         """Returns the modulated convolution; with ``activation`` the FusedLeakyReLU (bias,
@@ -212,13 +229,7 @@ class ModulatedConv2d(nn.Module):
             # (path-length regularisation), which must stay connected to the caller's graph
             input = nhwc(input)
         s = (self.modulation(style) if modulation is None else modulation).contiguous()   # (B, Cin)
-        def derived():
-            ws = self.weight[0] * self.scale                         # temp, never the leaf (see op/conv.py)
-            wsq = ws.pow(2).sum(dim=(2, 3)) if self.demodulate else None          # (Cout, Cin)
-            # upsampling branch: (taps, Cin, Cout), the packed weight of the stride-2 conv it is the adjoint of
-            return PackWeight.apply(ws, bool(self.upsample), 1.0), wsq
-
-        wp, wsq = cached(self.weight, "modconv", derived)
+        wp, wsq = self.derived_weights()
         d = None
         if self.demodulate:
             d = torch.rsqrt((s * s) @ wsq.t() + self.eps)            # (B, Cout)
@@ -309,3 +320,19 @@ class ToRGB(nn.Module):
         if skip is not None:
             out = out + self.upsample(skip)
         return out
+
+
+def warm_weight_cache(*modules):
+    """Build, on the CURRENT stream, every per-iteration cached tensor derived from the parameters of ``modules``
+    (packed / scaled weights; op/conv.py step cache).  Call it before branching onto side streams: a cache entry is
+    created on the stream of its first use, and another stream that reads it would not be ordered after the kernels
+    that produced it."""
+    for mod in modules:
+        for m in mod.modules():
+            fn = getattr(m, "derived_weights", None)
+            if fn is None:
+                continue
+            out = fn()
+            wp = out[0] if isinstance(out, tuple) else out
+            if torch.is_tensor(wp) and wp.dim() == 3 and wp.requires_grad and torch.is_grad_enabled():
+                _ops.dgrad_weights(wp)           # the backward pass will ask for it, possibly from another stream

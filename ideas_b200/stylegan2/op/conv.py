@@ -136,17 +136,23 @@ def _fwd(x, wp, g: Geom, in_scale=None, out_scale=None, bias=None, act=_lib.ACT_
 
 def _dgrad(dy, wp, g: Geom, in_scale=None, out_scale=None, impl=None):
     """dx (N,C,H,W) = in_scale * conv_transpose(out_scale * dy, w)."""
-    def repack():
-        t = torch.empty_like(wp)
-        _lib.call("ideas_repack_dgrad", ptr(t), ptr(wp), g.K, g.C, g.kh * g.kw, stream_ptr(dy))
-        return t
-
-    wpt = cached(wp, "dgrad", repack, immutable=True)
+    wpt = dgrad_weights(wp)
     dx = empty_nhwc(g.N, g.C, g.H, g.W, dy)
     _lib.call("ideas_conv2d_dgrad", ptr(dx), ptr(dy), ptr(wpt), ptr(in_scale), ptr(out_scale), ptr(None),
               g.N, g.H, g.W, g.C, g.K, g.kh, g.kw, g.stride, g.pad, g.OH, g.OW, _lib.ACT_NONE, 0.2, 1.0,
               DEFAULT_IMPL if impl is None else impl, stream_ptr(dy))
     return dx
+
+
+def dgrad_weights(wp):
+    """The data-gradient operand of a packed weight (taps, K, C) -> (taps reversed, C, K); built once per packed
+    weight inside a step_scope (on the stream of the first caller: see model.warm_weight_cache)."""
+    def repack():
+        t = torch.empty_like(wp)
+        _lib.call("ideas_repack_dgrad", ptr(t), ptr(wp), wp.shape[1], wp.shape[2], wp.shape[0], stream_ptr(wp))
+        return t
+
+    return cached(wp, "dgrad", repack, immutable=True)
 
 
 def _wgrad(x, dy, g: Geom, in_scale=None, out_scale=None, impl=None):

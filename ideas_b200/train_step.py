@@ -23,6 +23,7 @@ from torch.nn import functional as F
 
 from . import _lib
 from .models import init_model
+from .stylegan2.model import warm_weight_cache
 from .utils import (accumulate, d_logistic_loss, d_r1_loss, draw_crops, g_nonsaturating_loss, patchify_image,
                     requires_grad)
 
@@ -107,10 +108,12 @@ class Trainer:
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
-                 prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = False):
+                 prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = False,
+                 concurrent_generator: bool = False):
         self.args = args
         self.batch_generator = bool(batch_generator)
         self.split_dreal = bool(split_dreal) and not self.batch_generator
+        self.concurrent_generator = bool(concurrent_generator)
         self.device = torch.device(device)
         self.cuda_graphs = bool(cuda_graphs and self.device.type == "cuda")
         # independent sub-graphs of one iteration (Dreal on the real batch, the co-occurrence branch, the
@@ -345,7 +348,20 @@ class Trainer:
         three times the working set the activations and weight slabs of consecutive kernels no longer meet in the
         126 MB L2, and the E(container) branch can no longer start under the third call.  Off by default."""
         if not self.batch_generator:
-            xs = self.nets["G"](S1, T1), self.nets["G"](S2, T1), self.nets["G"](S2, T2)
+            if self.concurrent_generator and self.multi_stream:
+                # the three calls are independent chains of tensor-bound and HBM-bound kernels: on three streams the
+                # blur / activation kernels of one call run under the convolutions of another (autograd replays the
+                # same streams in backward)
+                with self._fork(2, S2, T1):
+                    x2 = self.nets["G"](S2, T1)
+                with self._fork(3, S2, T2):
+                    x3 = self.nets["G"](S2, T2)
+                x1 = self.nets["G"](S1, T1)
+                self._join(2, x2)
+                self._join(3, x3)
+                xs = (x1, x2, x3)
+            else:
+                xs = self.nets["G"](S1, T1), self.nets["G"](S2, T1), self.nets["G"](S2, T2)
             return xs, (None if self.split_dreal else torch.cat(xs, 0))
         hat = self.nets["G"](torch.cat((S1, S2, S2), 0), torch.cat((T1, T1, T2), 0))
         return hat.chunk(3, 0), hat
@@ -393,6 +409,10 @@ class Trainer:
         fake_boxes = crops("fake_crops_d", a.n_crop)
         real_boxes = crops("real_crops_d", a.n_crop)
         ref_boxes = crops("ref_crops_d", a.ref_crop * a.n_crop)
+        if self.multi_stream:
+            # cached packed weights are created on the stream of their first use: build those of the networks that run
+            # on side streams (and again on this one) here, so every stream that reads them is ordered after them
+            warm_weight_cache(t["Dreal"], t["Dco"], t["G"])
         with self._fork(0, X):                                   # Dreal on the real batch needs nothing from E / G
             real_pred = t["Dreal"](X)
         with self._fork(1, X):                                   # so do the real / reference patches of Dco
@@ -419,6 +439,8 @@ class Trainer:
         self.d_optim.step()
         # ---------------- lazy R1 (train.py:105-129)
         if r1:
+            if self.multi_stream:
+                warm_weight_cache(t["Dreal"], t["Dco"])          # the optimiser step above invalidated the cache
             Xr = X.detach().requires_grad_(True)
             r1_real = d_r1_loss(t["Dreal"](Xr), Xr)
             rp = real_patch.detach().requires_grad_(True)
@@ -438,6 +460,8 @@ class Trainer:
             requires_grad(t[k], True)
         for k in ("Dreal", "Dco", "Ddist"):
             requires_grad(t[k], False)
+        if self.multi_stream:
+            warm_weight_cache(t["E"], t["G"], t["Dco"], t["Ex"])
         S1, T1 = t["E"](X)
         Z = self._rand_like_Z(X, draws, "Z_g", device_rng)
         S2 = t["Gstru"](Z)

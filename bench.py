@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--case", default=None, help="run ONE roofline kernel alone (for ncu); see CASES in bench.py")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch-g", action="store_true", help="A/B: one batched Generator call per phase instead of three")
-    ap.add_argument("--split-dreal", action="store_true", help="A/B: Dreal on the three fake batches separately")
+    ap.add_argument("--no-split-dreal", action="store_true", help="A/B: Dreal on the concatenated fake batch (one call)")
     ap.add_argument("--no-concurrent-g", action="store_true", help="A/B: the three Generator calls of a phase on ONE stream")
     ap.add_argument("--single-stream", action="store_true", help="A/B: capture the step on one stream (no side-stream branches)")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
@@ -419,7 +419,7 @@ def run_ours(args):
     targs = default_args(batch_size=B, image_size=S)
     tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
                  multi_stream=False if args.single_stream else None,
-                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=args.split_dreal,
+                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=not args.no_split_dreal,
                  concurrent_generator=not args.no_concurrent_g)
     tr.broadcast_parameters(0)
     import random

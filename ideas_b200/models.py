@@ -356,12 +356,18 @@ class CooccurenceDiscriminator(nn.Module):
             EqualLinear(channel * 32, channel * 16, activation="fused_lrelu"),
             EqualLinear(channel * 16, 1))
 
+    def reference_code(self, reference, ref_batch):
+        """The ``ref_input`` that forward() derives from the reference patches (models.py:417-420): their encoder
+        features averaged over the ``ref_batch`` patches of each image.  Exposed so a caller can evaluate it early,
+        on another stream, and pass it back as ``ref_input``."""
+        ref = self.encoder(reference)
+        _, c, h, w = ref.shape
+        return ref.reshape(-1, ref_batch, c, h, w).mean(1)
+
     def forward(self, input, reference=None, ref_batch=None, ref_input=None):
         feat = self.encoder(input)
         if ref_input is None:
-            ref = self.encoder(reference)
-            _, c, h, w = ref.shape
-            ref_input = ref.reshape(-1, ref_batch, c, h, w).mean(1)
+            ref_input = self.reference_code(reference, ref_batch)
         out = torch.flatten(torch.cat((feat, ref_input), 1), 1)
         return self.linear(out), ref_input
 

@@ -334,5 +334,7 @@ def warm_weight_cache(*modules):
                 continue
             out = fn()
             wp = out[0] if isinstance(out, tuple) else out
-            if torch.is_tensor(wp) and wp.dim() == 3 and wp.requires_grad and torch.is_grad_enabled():
-                _ops.dgrad_weights(wp)           # the backward pass will ask for it, possibly from another stream
+            if torch.is_tensor(wp) and wp.dim() == 3:
+                # the backward pass -- and the forward of an up-sampling modulated conv, which IS a data gradient --
+                # will ask for the transposed copy, possibly from another stream
+                _ops.dgrad_weights(wp)

@@ -109,11 +109,12 @@ class Trainer:
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
                  prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = True,
-                 concurrent_generator: bool = True):
+                 concurrent_generator: bool = True, early_generator: bool = False):
         self.args = args
         self.batch_generator = bool(batch_generator)
         self.split_dreal = bool(split_dreal) and not self.batch_generator and self.multi_stream
         self.concurrent_generator = bool(concurrent_generator)
+        self.early_generator = bool(early_generator)
         self.device = torch.device(device)
         self.cuda_graphs = bool(cuda_graphs and self.device.type == "cuda")
         # independent sub-graphs of one iteration (Dreal on the real batch, the co-occurrence branch, the
@@ -340,7 +341,7 @@ class Trainer:
         with step_scope():                 # packed weights are built once per optimiser step, not once per call
             return self._iteration(X, r1, late, draws, boxes, device_rng)
 
-    def _generate3(self, S1, S2, T1, T2):
+    def _generate3(self, S1, S2, T1, T2, streams=(2, 3)):
         """hat_X1, hat_X2, hat_X3 = G(S1,T1), G(S2,T1), G(S2,T2) (train.py:66-70,154-158) and their concatenation
         (the argument of Dreal, train.py:73,161).  G is per-sample independent (no batch statistics), so the three
         calls may run as ONE call on the concatenated batch (``batch_generator=True``: same values and gradients, a
@@ -352,13 +353,13 @@ class Trainer:
                 # the three calls are independent chains of tensor-bound and HBM-bound kernels: on three streams the
                 # blur / activation kernels of one call run under the convolutions of another (autograd replays the
                 # same streams in backward).  Measured: 283.5 vs 292.9 ms per step.
-                with self._fork(2, S2, T1):
+                with self._fork(streams[0], S2, T1):
                     x2 = self.nets["G"](S2, T1)
-                with self._fork(3, S2, T2):
+                with self._fork(streams[1], S2, T2):
                     x3 = self.nets["G"](S2, T2)
                 x1 = self.nets["G"](S1, T1)
-                self._join(2, x2)
-                self._join(3, x3)
+                self._join(streams[0], x2)
+                self._join(streams[1], x3)
                 xs = (x1, x2, x3)
             else:
                 xs = self.nets["G"](S1, T1), self.nets["G"](S2, T1), self.nets["G"](S2, T2)
@@ -447,6 +448,35 @@ class Trainer:
         D_texture_loss = d_logistic_loss(real_texture_pred, fake_texture_pred)
         D_dist_loss = d_logistic_loss(t["Ddist"](T2), t["Ddist"](T1))
         loss.update(D_real_loss=D_real_loss, D_texture_loss=D_texture_loss, D_dist_loss=D_dist_loss)
+
+        def generator_forward(g_streams, ref_stream):
+            """First part of the G / E / Ex phase (train.py:144-158): everything that does not read a discriminator."""
+            Zg = self._rand_like_Z(X, draws, "Z_g", device_rng)
+            fb = crops("fake_crops_g", a.n_crop)
+            rb = crops("ref_crops_g", a.ref_crop * a.n_crop)
+            ref_code = None
+            if self.multi_stream:
+                # the reference-patch code of the co-occurrence branch depends on X alone (and, with the
+                # discriminators frozen or simply not differentiated w.r.t. it, has no backward): evaluate it early
+                with self._fork(ref_stream, X), torch.no_grad():
+                    ref_code = t["Dco"].reference_code(patchify_image(X, a.ref_crop * a.n_crop, crops=rb), a.ref_crop)
+            S1g, T1g = t["E"](X)
+            S2g = t["Gstru"](Zg)
+            T2g = self._rand_like_T(T1g, draws, "T2_g")
+            hats, hall = self._generate3(S1g, S2g, T1g, T2g, streams=g_streams)
+            return dict(Z=Zg, fake_boxes=fb, ref_boxes=rb, ref_code=ref_code, ref_stream=ref_stream, S1=S1g, T1=T1g,
+                        S2=S2g, T2=T2g, hats=hats, hat_all=hall)
+
+        early = None
+        if self.early_generator and self.multi_stream and not r1:
+            # The generator-side forward of the next phase reads no discriminator, and E / G / Gstru do not change
+            # in this one: start it on its own streams now, under the discriminators' backward pass and optimiser
+            # step.  Same values, same order of random draws (the backward pass draws nothing).
+            for k in EMA_KEYS:
+                requires_grad(t[k], True)
+            warm_weight_cache(t["E"], t["Gstru"], t["G"])
+            with self._fork(4, X):
+                early = generator_forward((5, 6), 7)
         self._zero_grad("d")
         (D_real_loss + D_texture_loss + D_dist_loss).backward()
         self.d_optim.step()
@@ -475,20 +505,16 @@ class Trainer:
             requires_grad(t[k], False)
         if self.multi_stream:
             warm_weight_cache(t["E"], t["G"], t["Dco"], t["Ex"], t["Dreal"])
-        # host-side draws in the reference's order (train.py:147-148 then :168-169); T2 comes from the device generator
-        Z = self._rand_like_Z(X, draws, "Z_g", device_rng)
-        fake_boxes = crops("fake_crops_g", a.n_crop)
-        ref_boxes = crops("ref_crops_g", a.ref_crop * a.n_crop)
-        ref_input_g = None
-        if self.multi_stream:
-            # the reference-patch code of the co-occurrence branch depends on X alone (and, with the discriminators
-            # frozen, has no backward): evaluate it under E(X) instead of after the Generator calls
-            with self._fork(1, X):
-                ref_input_g = t["Dco"].reference_code(patchify_image(X, a.ref_crop * a.n_crop, crops=ref_boxes), a.ref_crop)
-        S1, T1 = t["E"](X)
-        S2 = t["Gstru"](Z)
-        T2 = self._rand_like_T(T1, draws, "T2_g")
-        (hat_X1, hat_X2, hat_X3), hat_all = self._generate3(S1, S2, T1, T2)
+        if early is None:
+            gf = generator_forward((2, 3), 1)
+        else:
+            gf = early
+            self._join(4, gf["S1"], gf["T1"], gf["S2"], gf["T2"], gf["Z"], *gf["hats"])
+        if gf["ref_code"] is not None and gf["ref_stream"] != 1:
+            self._join(gf["ref_stream"], gf["ref_code"])
+        Z, fake_boxes, ref_boxes, ref_input_g = gf["Z"], gf["fake_boxes"], gf["ref_boxes"], gf["ref_code"]
+        S1, T1, S2, T2, hat_all = gf["S1"], gf["T1"], gf["S2"], gf["T2"], gf["hat_all"]
+        hat_X1, hat_X2, hat_X3 = gf["hats"]
         container = hat_X3 if late else hat_X2
         with self._fork(0, container, S2, Z):                    # E(container) -> Ex branch (train.py:178-189)
             hat_S2, _ = t["E"](container)

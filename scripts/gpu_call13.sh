@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/parity_errors.jsonl
 timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -6
 B="python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-library-baseline --no-roofline --no-e2e"
-for cfg in "default::" "nosplit::--no-split-dreal"; do
+for cfg in "default::" "nosplit::--no-split-dreal" "earlyg::--early-g"; do
   name=${cfg%%:*}; rest=${cfg#*:}; envs=${rest%%:*}; flags=${rest#*:}
   env $envs timeout 600 $B $flags 2> gpurun_out/r2_ab13_$name.err | python -c "
 import json,sys

@@ -112,7 +112,6 @@ class Trainer:
                  concurrent_generator: bool = True, early_generator: bool = False):
         self.args = args
         self.batch_generator = bool(batch_generator)
-        self.split_dreal = bool(split_dreal) and not self.batch_generator and self.multi_stream
         self.concurrent_generator = bool(concurrent_generator)
         self.early_generator = bool(early_generator)
         self.device = torch.device(device)
@@ -122,6 +121,7 @@ class Trainer:
         # the main branch, and autograd replays the same streams in backward.  Same arithmetic, same results.
         self.multi_stream = bool((self.cuda_graphs if multi_stream is None else multi_stream) and self.device.type == "cuda")
         self._side_streams: List[torch.cuda.Stream] = []
+        self.split_dreal = bool(split_dreal) and not self.batch_generator and self.multi_stream
         # train.py:214-216 runs Ex_loss.backward() over the whole retained graph, although only ex_optim.step()
         # follows: the gradients it adds to E / G / Gstru are discarded by the next g_optim.zero_grad().  With this
         # flag the second backward is restricted to Ex's parameters -- same parameter trajectory, ~10 % fewer FLOPs

@@ -420,7 +420,7 @@ def run_ours(args):
     targs = default_args(batch_size=B, image_size=S)
     tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
                  multi_stream=False if args.single_stream else None,
-                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=not args.no_split_dreal,
+                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=False if args.no_split_dreal else None,
                  concurrent_generator=not args.no_concurrent_g, early_generator=args.early_g)
     tr.broadcast_parameters(0)
     import random

@@ -27,6 +27,8 @@ from .stylegan2.model import warm_weight_cache
 from .utils import (accumulate, d_logistic_loss, d_r1_loss, draw_crops, g_nonsaturating_loss, patchify_image,
                     requires_grad)
 
+_AB_NO_DCO_HOIST = __import__("os").environ.get("IDEAS_AB_NO_DCO_HOIST", "0") == "1"     # measurement-only A/B switch
+
 NET_CLASSES = [("E", "DisentanglementEncoder"), ("G", "Generator"), ("Gstru", "StructureGenerator"),
                ("Ex", "TensorExtractor"), ("Dreal", "ImageLevelDiscriminator"),
                ("Dco", "CooccurenceDiscriminator"), ("Ddist", "DistributionDiscriminator")]
@@ -108,7 +110,7 @@ class Trainer:
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
-                 prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = True,
+                 prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: Optional[bool] = None,
                  concurrent_generator: bool = True, early_generator: bool = False):
         self.args = args
         self.batch_generator = bool(batch_generator)
@@ -121,7 +123,8 @@ class Trainer:
         # the main branch, and autograd replays the same streams in backward.  Same arithmetic, same results.
         self.multi_stream = bool((self.cuda_graphs if multi_stream is None else multi_stream) and self.device.type == "cuda")
         self._side_streams: List[torch.cuda.Stream] = []
-        self.split_dreal = bool(split_dreal) and not self.batch_generator and self.multi_stream
+        # None: split exactly when the pieces can run on different streams
+        self.split_dreal = (self.multi_stream if split_dreal is None else bool(split_dreal)) and not self.batch_generator
         # train.py:214-216 runs Ex_loss.backward() over the whole retained graph, although only ex_optim.step()
         # follows: the gradients it adds to E / G / Gstru are discarded by the next g_optim.zero_grad().  With this
         # flag the second backward is restricted to Ex's parameters -- same parameter trajectory, ~10 % fewer FLOPs
@@ -455,7 +458,7 @@ class Trainer:
             fb = crops("fake_crops_g", a.n_crop)
             rb = crops("ref_crops_g", a.ref_crop * a.n_crop)
             ref_code = None
-            if self.multi_stream:
+            if self.multi_stream and not _AB_NO_DCO_HOIST:
                 # the reference-patch code of the co-occurrence branch depends on X alone (and, with the
                 # discriminators frozen or simply not differentiated w.r.t. it, has no backward): evaluate it early
                 with self._fork(ref_stream, X), torch.no_grad():

@@ -269,7 +269,8 @@ def test_multi_stream_eager_step_is_race_free():
     draws = _draws(2, 1, 16, 128, 256, 256, 8, 4)
     runs = []
     for ms in (False, True, True):
-        tr = Trainer(default_args(**cfg), device="cuda", seed=13, fused_adam=False, multi_stream=ms)
+        # same arithmetic on both sides (Dreal on the three fake batches separately): only the streams differ
+        tr = Trainer(default_args(**cfg), device="cuda", seed=13, fused_adam=False, multi_stream=ms, split_dreal=True)
         lo = tr.step(X, 1, draws)
         torch.cuda.synchronize()
         runs.append({k: float(v) for k, v in lo.items()})
@@ -296,7 +297,7 @@ def test_graph_replay_multi_stream_matches_single_stream():
     for ms in (False, True):
         torch.manual_seed(21)
         random.seed(21)
-        tr = Trainer(default_args(**cfg), device="cuda", seed=9, cuda_graphs=True, multi_stream=ms)
+        tr = Trainer(default_args(**cfg), device="cuda", seed=9, cuda_graphs=True, multi_stream=ms, split_dreal=True)
         torch.manual_seed(22)
         random.seed(22)
         out = []

@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--case", default=None, help="run ONE roofline kernel alone (for ncu); see CASES in bench.py")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch-g", action="store_true", help="A/B: one batched Generator call per phase instead of three")
-    ap.add_argument("--no-split-dreal", action="store_true", help="A/B: Dreal on the concatenated fake batch (one call)")
+    ap.add_argument("--split-dreal", action="store_true", help="A/B: Dreal on the three fake batches separately, on the generator streams")
     ap.add_argument("--no-concurrent-g", action="store_true", help="A/B: the three Generator calls of a phase on ONE stream")
     ap.add_argument("--early-g", action="store_true", help="A/B: start the G phase's generator-side forward under the D backward")
     ap.add_argument("--single-stream", action="store_true", help="A/B: capture the step on one stream (no side-stream branches)")
@@ -189,11 +189,18 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
-def time_kernel(fn, iters=20, warm=3):
+def time_kernel(fn, iters=20, warm=3, warm_ms=60.0):
+    """Average launch time after a warm-up of at least ``warm`` launches AND ``warm_ms`` of GPU time (the clocks of
+    an idle GPU take a few milliseconds of load to come up; three sub-millisecond launches are not enough)."""
     import torch
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    while (time.perf_counter() - t0) * 1e3 < warm_ms:
+        for _ in range(4):
+            fn()
+        torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
@@ -360,7 +367,7 @@ def roofline_sections(peaks, peak_kind):
     half_bf16 = peaks["bf16_tflops"] * 0.5
     for key, case in CASES.items():
         fn, work, bound, desc = make_case(case)
-        t = time_kernel(fn, iters=10, warm=3)
+        t = time_kernel(fn, iters=20, warm=3)
         tr = traffic.get(case, {})
         if bound == "tensor":
             ach = work / t / 1e12
@@ -420,7 +427,7 @@ def run_ours(args):
     targs = default_args(batch_size=B, image_size=S)
     tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
                  multi_stream=False if args.single_stream else None,
-                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=False if args.no_split_dreal else None,
+                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=args.split_dreal,
                  concurrent_generator=not args.no_concurrent_g, early_generator=args.early_g)
     tr.broadcast_parameters(0)
     import random

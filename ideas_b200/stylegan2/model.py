@@ -320,21 +320,3 @@ class ToRGB(nn.Module):
         if skip is not None:
             out = out + self.upsample(skip)
         return out
-
-
-def warm_weight_cache(*modules):
-    """Build, on the CURRENT stream, every per-iteration cached tensor derived from the parameters of ``modules``
-    (packed / scaled weights; op/conv.py step cache).  Call it before branching onto side streams: a cache entry is
-    created on the stream of its first use, and another stream that reads it would not be ordered after the kernels
-    that produced it."""
-    for mod in modules:
-        for m in mod.modules():
-            fn = getattr(m, "derived_weights", None)
-            if fn is None:
-                continue
-            out = fn()
-            wp = out[0] if isinstance(out, tuple) else out
-            if torch.is_tensor(wp) and wp.dim() == 3:
-                # the backward pass -- and the forward of an up-sampling modulated conv, which IS a data gradient --
-                # will ask for the transposed copy, possibly from another stream
-                _ops.dgrad_weights(wp)

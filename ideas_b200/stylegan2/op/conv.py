@@ -46,6 +46,9 @@ def set_default_impl(impl: int) -> int:
 
 
 # --------------------------------------------------------------------------- per-step cache of derived weights
+_AB_NO_CACHE = os.environ.get("IDEAS_AB_NO_CACHE", "0") == "1"      # measurement / debugging switch
+
+
 class _StepCache:
     """Packed weights (and the other tensors derived from a parameter alone) are functions of the parameter, which
     changes once per optimiser step -- yet a training iteration runs E twice, G and Dreal three to six times.  Inside
@@ -54,7 +57,10 @@ class _StepCache:
     from a parameter are keyed by the parameter's ``_version`` AND by an epoch that the owner of the scope advances
     after every optimiser step (``invalidate_step_cache``; fused Adam updates parameters without touching their
     version counters).  The cache is dropped when the scope exits, so nothing derived from stale weights -- or
-    living in a CUDA graph's private memory pool -- can be seen outside the iteration that built it."""
+    living in a CUDA graph's private memory pool -- can be seen outside the iteration that built it.  Entries are
+    per CUDA stream (see ``cached``): sharing one packed weight between the side-stream branches of a captured
+    iteration produced wrong results under graph replay (scripts/debug_graph_streams.py), and a few extra
+    microsecond-sized pack kernels per stream are cheaper than any cross-stream ordering of cached tensors."""
     depth = 0
     epoch = 0
     store: dict = {}
@@ -82,10 +88,13 @@ class step_scope:
 def cached(key: torch.Tensor, tag, build, immutable: bool = False):
     """``build()`` once per (key tensor, version, epoch, autograd mode, tag) inside a step_scope; plain call outside.
     ``immutable``: the key is a temporary that nothing updates in place (a packed copy), so the epoch is ignored."""
-    if _StepCache.depth == 0:
+    if _StepCache.depth == 0 or _AB_NO_CACHE:
         return build()
+    # the CUDA stream is part of the key: an entry is only ever read on the stream that wrote it, so branches of the
+    # iteration that run on side streams (train_step.py) never depend on another stream's kernels through the cache
+    sid = torch.cuda.current_stream(key.device).cuda_stream if key.is_cuda else 0
     k = (id(key), key._version, -1 if immutable else _StepCache.epoch,
-         bool(key.requires_grad and torch.is_grad_enabled()), tag)
+         bool(key.requires_grad and torch.is_grad_enabled()), sid, tag)
     hit = _StepCache.store.get(k)
     if hit is None:
         hit = (key, build())                 # holding ``key`` keeps id() unique while the entry lives

@@ -23,7 +23,6 @@ from torch.nn import functional as F
 
 from . import _lib
 from .models import init_model
-from .stylegan2.model import warm_weight_cache
 from .utils import (accumulate, d_logistic_loss, d_r1_loss, draw_crops, g_nonsaturating_loss, patchify_image,
                     requires_grad)
 
@@ -110,7 +109,7 @@ class Trainer:
 
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
-                 prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: Optional[bool] = None,
+                 prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = False,
                  concurrent_generator: bool = True, early_generator: bool = False):
         self.args = args
         self.batch_generator = bool(batch_generator)
@@ -123,8 +122,7 @@ class Trainer:
         # the main branch, and autograd replays the same streams in backward.  Same arithmetic, same results.
         self.multi_stream = bool((self.cuda_graphs if multi_stream is None else multi_stream) and self.device.type == "cuda")
         self._side_streams: List[torch.cuda.Stream] = []
-        # None: split exactly when the pieces can run on different streams
-        self.split_dreal = (self.multi_stream if split_dreal is None else bool(split_dreal)) and not self.batch_generator
+        self.split_dreal = bool(split_dreal) and not self.batch_generator
         # train.py:214-216 runs Ex_loss.backward() over the whole retained graph, although only ex_optim.step()
         # follows: the gradients it adds to E / G / Gstru are discarded by the next g_optim.zero_grad().  With this
         # flag the second backward is restricted to Ex's parameters -- same parameter trajectory, ~10 % fewer FLOPs
@@ -391,8 +389,8 @@ class Trainer:
         """Dreal(cat(hat_X1, hat_X2, hat_X3)) (train.py:73,161).  Dreal is per-sample independent (no minibatch-stddev
         layer, models.py:369-376), so with side streams the three fake batches each continue on the stream of the
         Generator call that produced them: five chains (three G -> Dreal, E(container) -> Ex, the co-occurrence
-        branch) keep the tensor pipe and HBM busy at the same time.  Measured: 265.5 ms per step, against 290.4 with
-        only the Generator calls concurrent and 297.8 with neither (same box)."""
+        branch) run at the same time.  Measured: no gain over one call on the concatenated batch (285.9 vs 285.6 ms per
+        step; a 265 ms reading of one run did not reproduce), so ``split_dreal`` is off by default."""
         if x_all is not None:
             return self.nets["Dreal"](x_all)
         if self.concurrent_generator and self.multi_stream:
@@ -426,10 +424,6 @@ class Trainer:
         fake_boxes = crops("fake_crops_d", a.n_crop)
         real_boxes = crops("real_crops_d", a.n_crop)
         ref_boxes = crops("ref_crops_d", a.ref_crop * a.n_crop)
-        if self.multi_stream:
-            # cached packed weights are created on the stream of their first use: build those of the networks that run
-            # on side streams (and again on this one) here, so every stream that reads them is ordered after them
-            warm_weight_cache(t["Dreal"], t["Dco"], t["G"])
         with self._fork(0, X):                                   # Dreal on the real batch needs nothing from E / G
             real_pred = t["Dreal"](X)
         with self._fork(1, X):                                   # so do the real / reference patches of Dco
@@ -477,7 +471,6 @@ class Trainer:
             # step.  Same values, same order of random draws (the backward pass draws nothing).
             for k in EMA_KEYS:
                 requires_grad(t[k], True)
-            warm_weight_cache(t["E"], t["Gstru"], t["G"])
             with self._fork(4, X):
                 early = generator_forward((5, 6), 7)
         self._zero_grad("d")
@@ -485,8 +478,6 @@ class Trainer:
         self.d_optim.step()
         # ---------------- lazy R1 (train.py:105-129)
         if r1:
-            if self.multi_stream:
-                warm_weight_cache(t["Dreal"], t["Dco"])          # the optimiser step above invalidated the cache
             Xr = X.detach().requires_grad_(True)
             r1_real = d_r1_loss(t["Dreal"](Xr), Xr)
             rp = real_patch.detach().requires_grad_(True)
@@ -506,8 +497,6 @@ class Trainer:
             requires_grad(t[k], True)
         for k in ("Dreal", "Dco", "Ddist"):
             requires_grad(t[k], False)
-        if self.multi_stream:
-            warm_weight_cache(t["E"], t["G"], t["Dco"], t["Ex"], t["Dreal"])
         if early is None:
             gf = generator_forward((2, 3), 1)
         else:

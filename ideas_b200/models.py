@@ -45,11 +45,13 @@ class EqualConvTranspose2d(nn.Module):
     def derived_weights(self):
         return packed_weight(self.weight, False, self.scale)
 
-    def forward(self, input, stride=None):
+    def forward(self, input, stride=None, weight_mul: float = 1.0):
         cin, cout, k, _ = self.weight.shape
         stride = self.stride if stride is None else stride
+        if weight_mul != 1.0 and self.bias is not None:
+            raise RuntimeError("EqualConvTranspose2d: weight_mul would not scale the bias")
         # (in, out, k, k) is the OIHW weight of the stride-s conv whose adjoint this layer is
-        wp = packed_weight(self.weight, False, self.scale)
+        wp = packed_weight(self.weight, False, self.scale * weight_mul)
         out = _ops.conv_transpose2d(input, wp, C_out=cout, kh=k, kw=k, stride=stride, pad=self.padding)
         if self.bias is not None:
             out = out + self.bias.view(1, -1, 1, 1)
@@ -122,11 +124,15 @@ class ConvLayer(nn.Sequential):
         super().__init__(*stages)
         self.padding = conv_pad
 
-    def forward(self, input, start=0, residual=None, res_scale=1.0):
+    def forward(self, input, start=0, residual=None, res_scale=1.0, gain_mul=1.0, weight_mul=1.0):
         """``start``: index of the first child to run (ResBlock fuses conv1's tail with conv2's leading Blur).
         ``residual``: the layer returns (layer(input) + residual) * res_scale.  When the layer ends in an
         activation-free convolution or in the blur of an up-sampling skip -- every skip path of the residual blocks
-        does -- the merge happens in that kernel's epilogue; otherwise it is one add_scale pass."""
+        does -- the merge happens in that kernel's epilogue; otherwise it is one add_scale pass.
+        ``gain_mul`` / ``weight_mul``: factor folded into the layer's fused activation gain / its bias-free
+        convolution's weights (``scalable()`` tells whether the layer's structure allows it)."""
+        if (gain_mul != 1.0 or weight_mul != 1.0) and not self.scalable(start):
+            raise RuntimeError("ConvLayer: this layer cannot absorb an output scale")
         mods = list(self)
         i, out = start, input
         while i < len(mods):
@@ -134,7 +140,7 @@ class ConvLayer(nn.Sequential):
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             last2, last1 = i + 2 >= len(mods), i + 1 >= len(mods)
             if isinstance(m, EqualConv2d) and isinstance(nxt, FusedLeakyReLU):
-                out = m(out, activation=nxt)          # one kernel: conv + bias + leaky ReLU
+                out = m(out, activation=nxt, gain_mul=gain_mul)          # one kernel: conv + bias + leaky ReLU
                 i += 2
             elif (isinstance(m, Blur) and isinstance(nxt, EqualConv2d) and nxt.weight.shape[2] == 1
                   and nxt.stride == 2 and nxt.padding == 0):
@@ -142,24 +148,24 @@ class ConvLayer(nn.Sequential):
                 # blur and decimate in one pass (upfirdn2d down=2) and run the 1x1 conv at the low resolution
                 low = upfirdn2d(out, m.kernel, down=2, pad=m.pad)
                 if residual is not None and last2:
-                    out, residual = nxt(low, stride=1, residual=residual, res_scale=res_scale), None
+                    out, residual = nxt(low, stride=1, residual=residual, res_scale=res_scale, weight_mul=weight_mul), None
                 else:
-                    out = nxt(low, stride=1)
+                    out = nxt(low, stride=1, weight_mul=weight_mul)
                 i += 2
             elif (isinstance(m, EqualConvTranspose2d) and isinstance(nxt, Blur) and m.weight.shape[2] == 1
                   and m.stride == 2 and m.padding == 0 and m.bias is None):
                 # 1x1 stride-2 transposed conv -> Blur (up-sampling skip): a bias-free 1x1 conv commutes with zero
                 # insertion, so convolve at the low resolution and let upfirdn2d(up=2) interleave the zeros on the
                 # fly (its trailing zero replaces one unit of right padding)
-                low = m(out, stride=1)
+                low = m(out, stride=1, weight_mul=weight_mul)
                 pad = (nxt.pad[0], nxt.pad[1] - 1)
                 if residual is not None and last2 and residual_ok(low, nxt.kernel, (2, 2), (1, 1)):
                     out, residual = upfirdn2d(low, nxt.kernel, up=2, pad=pad, residual=residual, res_scale=res_scale), None
                 else:
                     out = upfirdn2d(low, nxt.kernel, up=2, pad=pad)
                 i += 2
-            elif isinstance(m, EqualConv2d) and residual is not None and last1:
-                out, residual = m(out, residual=residual, res_scale=res_scale), None
+            elif isinstance(m, EqualConv2d) and last1 and (residual is not None or weight_mul != 1.0):
+                out, residual = m(out, residual=residual, res_scale=res_scale, weight_mul=weight_mul), None
                 i += 1
             else:
                 out = m(out)
@@ -167,6 +173,24 @@ class ConvLayer(nn.Sequential):
         if residual is not None:
             out = add_scale(out, residual, res_scale)
         return out
+
+
+def _conv_layer_scalable(layer, start=0):
+    """True when ``ConvLayer.forward(start=...)`` can fold an output factor into its kernels: the layer is
+    [Blur] -> conv -> FusedLeakyReLU (factor goes into the activation gain) or a bias-free, activation-free
+    [Blur ->] 1x1 conv / 1x1 transposed conv -> Blur (factor goes into the weights)."""
+    mods = list(layer)[start:]
+    convs = [m for m in mods if isinstance(m, (EqualConv2d, EqualConvTranspose2d))]
+    if len(convs) != 1:
+        return False
+    rest = [m for m in mods if not isinstance(m, (EqualConv2d, EqualConvTranspose2d, Blur, ReflectionPad2d))]
+    if not rest:
+        return convs[0].bias is None
+    return len(rest) == 1 and isinstance(rest[0], FusedLeakyReLU) and mods[-1] is rest[0] and convs[0].bias is None \
+        and isinstance(convs[0], EqualConv2d)
+
+
+ConvLayer.scalable = _conv_layer_scalable
 
 
 class StyledResBlock(nn.Module):
@@ -187,8 +211,14 @@ class StyledResBlock(nn.Module):
             # pass, and its style gradient comes out of conv1's activation backward for free (op/conv.py, ``post``)
             if m2 is None:
                 m2 = self.conv2.conv.modulation(style)
+            fold = self.skip is not None and self.skip.scalable()
             _, a_mod = self.conv1(input, style, noise, modulation=m1, post_modulation=m2)
-            out = self.conv2(a_mod, style, noise, modulation=m2, premodulated=True)
+            # (out + skip)/sqrt(2): the factor goes into conv2's activation gain (sqrt(2) * 1/sqrt(2)) and into the
+            # skip convolution's weights, so the merge is a plain sum in the skip path's epilogue and the backward
+            # pass has no scaling pass at all
+            out = self.conv2(a_mod, style, noise, modulation=m2, premodulated=True, gain_mul=_INV_SQRT2 if fold else 1.0)
+            if fold:
+                return self.skip(input, residual=out, res_scale=1.0, weight_mul=_INV_SQRT2)
         else:
             out = self.conv2(self.conv1(input, style, noise, modulation=m1), style, noise, modulation=m2)
         if self.skip is None:
@@ -216,9 +246,13 @@ class ResBlock(nn.Module):
             h = input
             for m in c1[:-2]:                      # ReflectionPad2d of the encoder blocks
                 h = m(h)
-            out = self.conv2(c1[-2].forward_act_blur(h, c1[-1], c2[0]), start=1)
+            fold = self.skip is not None and self.skip.scalable() and self.conv2.scalable(1)
+            out = self.conv2(c1[-2].forward_act_blur(h, c1[-1], c2[0]), start=1, gain_mul=_INV_SQRT2 if fold else 1.0)
         else:
-            out = self.conv2(self.conv1(input))
+            fold = input.is_cuda and self.skip is not None and self.skip.scalable() and self.conv2.scalable()
+            out = self.conv2(self.conv1(input), gain_mul=_INV_SQRT2 if fold else 1.0)
+        if fold:        # 1/sqrt(2) lives in conv2's activation gain and the skip's weights: the merge is a plain sum
+            return self.skip(input, residual=out, res_scale=1.0, weight_mul=_INV_SQRT2)
         if self.skip is None:
             return add_scale(out, input, _INV_SQRT2)
         return self.skip(input, residual=out, res_scale=_INV_SQRT2)      # (out + skip)/sqrt(2) in the skip's epilogue

@@ -99,20 +99,25 @@ class EqualConv2d(nn.Module):
         return packed_weight(self.weight, False, self.scale)
 
     def forward(self, input, activation: FusedLeakyReLU | None = None, stride: int | None = None, residual=None,
-                res_scale: float = 1.0):
+                res_scale: float = 1.0, gain_mul: float = 1.0, weight_mul: float = 1.0):
         """``activation``: a FusedLeakyReLU module to fuse into the conv epilogue.  ``stride`` overrides the
         module's stride (ConvLayer folds the decimation of a 1x1 stride-2 conv into the preceding blur).
-        ``residual``: merged in the epilogue, (conv(x) + bias + residual) * res_scale (activation-free only)."""
+        ``residual``: merged in the epilogue, (conv(x) + bias + residual) * res_scale (activation-free only).
+        ``gain_mul`` multiplies the fused activation's gain, ``weight_mul`` the (bias-free) convolution's weights:
+        a residual block folds its 1/sqrt(2) into them (models.py), so the merge itself is a plain sum."""
         k = self.weight.shape[2]
         stride = self.stride if stride is None else stride
-        wp = packed_weight(self.weight, False, self.scale)
+        if weight_mul != 1.0 and self.bias is not None:
+            raise RuntimeError("EqualConv2d: weight_mul would not scale the bias")
+        wp = packed_weight(self.weight, False, self.scale * weight_mul)
         if activation is not None:
             if self.bias is not None:
                 raise RuntimeError("EqualConv2d: a fused activation brings its own bias")
             if residual is not None:
                 raise RuntimeError("EqualConv2d: residual merge is available without a fused activation only")
             return _ops.conv2d(input, wp, activation.bias, K=self.weight.shape[0], kh=k, kw=k, stride=stride,
-                               pad=self.padding, act=True, alpha=activation.negative_slope, gain=activation.scale)
+                               pad=self.padding, act=True, alpha=activation.negative_slope,
+                               gain=activation.scale * gain_mul)
         return _ops.conv2d(input, wp, self.bias, K=self.weight.shape[0], kh=k, kw=k, stride=stride,
                            pad=self.padding, residual=residual, res_scale=res_scale)
 
@@ -215,7 +220,7 @@ class ModulatedConv2d(nn.Module):
         return cached(self.weight, "modconv", build)
 
     def forward(self, input, style, activation: FusedLeakyReLU | None = None, modulation: torch.Tensor | None = None,
-                premodulated: bool = False, post_modulation: torch.Tensor | None = None):
+                premodulated: bool = False, post_modulation: torch.Tensor | None = None, gain_mul: float = 1.0):
         """Returns the modulated convolution; with ``activation`` the FusedLeakyReLU (bias,
         slope, gain) is applied inside the same kernels (StyledConv passes its own).  ``modulation``: the
         per-sample channel scales s = self.modulation(style), when the caller has already computed them (the
@@ -236,7 +241,9 @@ class ModulatedConv2d(nn.Module):
         act = activation is not None
         bias = activation.bias if act else None
         alpha = activation.negative_slope if act else 0.2
-        gain = activation.scale if act else 1.0
+        gain = activation.scale * gain_mul if act else 1.0          # gain_mul: see EqualConv2d.forward
+        if gain_mul != 1.0 and not act:
+            raise RuntimeError("ModulatedConv2d: gain_mul needs the fused activation")
         if self.upsample:
             if premodulated:
                 raise RuntimeError("ModulatedConv2d: the up-sampling branch modulates its own input")
@@ -302,9 +309,9 @@ class StyledConv_without_noise(nn.Module):
                                     blur_kernel=blur_kernel, demodulate=demodulate)
         self.activate = FusedLeakyReLU(out_channel)
 
-    def forward(self, input, style, noise=None, modulation=None, premodulated=False, post_modulation=None):
+    def forward(self, input, style, noise=None, modulation=None, premodulated=False, post_modulation=None, gain_mul=1.0):
         return self.conv(input, style, activation=self.activate, modulation=modulation, premodulated=premodulated,
-                         post_modulation=post_modulation)
+                         post_modulation=post_modulation, gain_mul=gain_mul)
 
 
 class ToRGB(nn.Module):

@@ -446,23 +446,19 @@ class Trainer:
         D_dist_loss = d_logistic_loss(t["Ddist"](T2), t["Ddist"](T1))
         loss.update(D_real_loss=D_real_loss, D_texture_loss=D_texture_loss, D_dist_loss=D_dist_loss)
 
-        def generator_forward(g_streams, ref_stream):
+        def generator_draws():
+            """Host-side draws of the G / E / Ex phase in the reference's order (train.py:147-148 then :168-169)."""
+            return (self._rand_like_Z(X, draws, "Z_g", device_rng), crops("fake_crops_g", a.n_crop),
+                    crops("ref_crops_g", a.ref_crop * a.n_crop))
+
+        def generator_forward(g_streams, drawn):
             """First part of the G / E / Ex phase (train.py:144-158): everything that does not read a discriminator."""
-            Zg = self._rand_like_Z(X, draws, "Z_g", device_rng)
-            fb = crops("fake_crops_g", a.n_crop)
-            rb = crops("ref_crops_g", a.ref_crop * a.n_crop)
-            ref_code = None
-            if self.multi_stream and not _AB_NO_DCO_HOIST:
-                # the reference-patch code of the co-occurrence branch depends on X alone (and, with the
-                # discriminators frozen or simply not differentiated w.r.t. it, has no backward): evaluate it early
-                with self._fork(ref_stream, X), torch.no_grad():
-                    ref_code = t["Dco"].reference_code(patchify_image(X, a.ref_crop * a.n_crop, crops=rb), a.ref_crop)
+            Zg, fb, rb = drawn
             S1g, T1g = t["E"](X)
             S2g = t["Gstru"](Zg)
             T2g = self._rand_like_T(T1g, draws, "T2_g")
             hats, hall = self._generate3(S1g, S2g, T1g, T2g, streams=g_streams)
-            return dict(Z=Zg, fake_boxes=fb, ref_boxes=rb, ref_code=ref_code, ref_stream=ref_stream, S1=S1g, T1=T1g,
-                        S2=S2g, T2=T2g, hats=hats, hat_all=hall)
+            return dict(Z=Zg, fake_boxes=fb, ref_boxes=rb, S1=S1g, T1=T1g, S2=S2g, T2=T2g, hats=hats, hat_all=hall)
 
         early = None
         if self.early_generator and self.multi_stream and not r1:
@@ -472,8 +468,9 @@ class Trainer:
             # 299.6 ms per step.
             for k in EMA_KEYS:
                 requires_grad(t[k], True)
-            with self._fork(4, X):
-                early = generator_forward((5, 6), 7)
+            drawn = generator_draws()
+            with self._fork(4, X, drawn[0]):
+                early = generator_forward((5, 6), drawn)
         self._zero_grad("d")
         (D_real_loss + D_texture_loss + D_dist_loss).backward()
         self.d_optim.step()
@@ -498,14 +495,22 @@ class Trainer:
             requires_grad(t[k], True)
         for k in ("Dreal", "Dco", "Ddist"):
             requires_grad(t[k], False)
+        def reference_code(rb):
+            # the reference-patch code of the co-occurrence branch depends on X and the (now updated, frozen)
+            # discriminator alone and has no backward: evaluate it on the branch's stream before the Generator calls
+            with self._fork(1, X), torch.no_grad():
+                return t["Dco"].reference_code(patchify_image(X, a.ref_crop * a.n_crop, crops=rb), a.ref_crop)
+
+        hoist = self.multi_stream and not _AB_NO_DCO_HOIST
         if early is None:
-            gf = generator_forward((2, 3), 1)
+            drawn = generator_draws()
+            ref_input_g = reference_code(drawn[2]) if hoist else None
+            gf = generator_forward((2, 3), drawn)
         else:
             gf = early
+            ref_input_g = reference_code(gf["ref_boxes"]) if hoist else None
             self._join(4, gf["S1"], gf["T1"], gf["S2"], gf["T2"], gf["Z"], *gf["hats"])
-        if gf["ref_code"] is not None and gf["ref_stream"] != 1:
-            self._join(gf["ref_stream"], gf["ref_code"])
-        Z, fake_boxes, ref_boxes, ref_input_g = gf["Z"], gf["fake_boxes"], gf["ref_boxes"], gf["ref_code"]
+        Z, fake_boxes, ref_boxes = gf["Z"], gf["fake_boxes"], gf["ref_boxes"]
         S1, T1, S2, T2, hat_all = gf["S1"], gf["T1"], gf["S2"], gf["T2"], gf["hat_all"]
         hat_X1, hat_X2, hat_X3 = gf["hats"]
         container = hat_X3 if late else hat_X2

@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--batch-g", action="store_true", help="A/B: one batched Generator call per phase instead of three")
     ap.add_argument("--split-dreal", action="store_true", help="A/B: Dreal on the three fake batches separately, on the generator streams")
     ap.add_argument("--no-concurrent-g", action="store_true", help="A/B: the three Generator calls of a phase on ONE stream")
-    ap.add_argument("--no-early-g", action="store_true", help="A/B: do not start the G phase's generator-side forward under the D backward")
+    ap.add_argument("--early-g", action="store_true", help="A/B: start the G phase's generator-side forward under the D backward")
     ap.add_argument("--single-stream", action="store_true", help="A/B: capture the step on one stream (no side-stream branches)")
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--prune-dead-backward", action="store_true",
@@ -428,7 +428,7 @@ def run_ours(args):
     tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
                  multi_stream=False if args.single_stream else None,
                  prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=args.split_dreal,
-                 concurrent_generator=not args.no_concurrent_g, early_generator=not args.no_early_g)
+                 concurrent_generator=not args.no_concurrent_g, early_generator=args.early_g)
     tr.broadcast_parameters(0)
     import random
     torch.manual_seed(1000 + rank)                   # per-rank data / Z / T2 / crops

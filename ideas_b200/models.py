@@ -21,7 +21,7 @@ from torch import nn
 from .stylegan2.model import (Blur, EqualConv2d, EqualLinear, ScaledLeakyReLU,
                               StyledConv_without_noise as StyledConv)
 from .stylegan2.op import FusedLeakyReLU, upfirdn2d
-from .stylegan2.op.upfirdn2d import residual_ok
+from .stylegan2.op.upfirdn2d import SplitDown, residual_ok
 from .stylegan2.op import conv as _ops
 from .stylegan2.op.conv import cached, packed_weight
 from .stylegan2.op.linear import matmul_nt
@@ -124,7 +124,7 @@ class ConvLayer(nn.Sequential):
         super().__init__(*stages)
         self.padding = conv_pad
 
-    def forward(self, input, start=0, residual=None, res_scale=1.0, gain_mul=1.0, weight_mul=1.0):
+    def forward(self, input, start=0, residual=None, res_scale=1.0, gain_mul=1.0, weight_mul=1.0, pre_low=None):
         """``start``: index of the first child to run (ResBlock fuses conv1's tail with conv2's leading Blur).
         ``residual``: the layer returns (layer(input) + residual) * res_scale.  When the layer ends in an
         activation-free convolution or in the blur of an up-sampling skip -- every skip path of the residual blocks
@@ -146,7 +146,8 @@ class ConvLayer(nn.Sequential):
                   and nxt.stride == 2 and nxt.padding == 0):
                 # Blur -> 1x1 stride-2 conv (down-sampling skip): the conv reads every other blurred pixel, so
                 # blur and decimate in one pass (upfirdn2d down=2) and run the 1x1 conv at the low resolution
-                low = upfirdn2d(out, m.kernel, down=2, pad=m.pad)
+                # ``pre_low``: the caller already ran this blur + decimation on the layer's input (ResBlock, SplitDown)
+                low = pre_low if (pre_low is not None and i == start) else upfirdn2d(out, m.kernel, down=2, pad=m.pad)
                 if residual is not None and last2:
                     out, residual = nxt(low, stride=1, residual=residual, res_scale=res_scale, weight_mul=weight_mul), None
                 else:
@@ -237,8 +238,24 @@ class ResBlock(nn.Module):
             self.skip = ConvLayer(in_channel, out_channel, 1, downsample=downsample, blur_kernel=blur_kernel,
                                   bias=False, activate=False)
 
+    def _down_skip(self):
+        """(blur, conv) when the skip path is Blur -> bias-free 1x1 stride-2 conv, else None."""
+        sk = list(self.skip) if self.skip is not None else []
+        if (len(sk) == 2 and isinstance(sk[0], Blur) and isinstance(sk[1], EqualConv2d) and sk[1].weight.shape[2] == 1
+                and sk[1].stride == 2 and sk[1].padding == 0 and sk[1].bias is None):
+            return sk[0], sk[1]
+        return None
+
     def forward(self, input):
         c1, c2 = list(self.conv1), list(self.conv2)
+        low = None
+        block_input = input
+        ds = self._down_skip() if input.is_cuda else None
+        if ds is not None and input.requires_grad and input.shape[1] % 4 == 0:
+            # the block input feeds the main path and the skip's blur: one node for both, whose backward adds the two
+            # gradients inside the blur's adjoint kernel (op/upfirdn2d.py SplitDown)
+            p = ds[0].pad
+            input, low = SplitDown.apply(input, ds[0].kernel, (p[0], p[1], p[0], p[1]))
         if (input.is_cuda and isinstance(c2[0], Blur) and len(c1) >= 2 and isinstance(c1[-1], FusedLeakyReLU)
                 and isinstance(c1[-2], EqualConv2d) and c1[-2].bias is None):
             # conv1 -> FusedLeakyReLU -> Blur as one autograd node: its backward fuses the blur's and the
@@ -252,10 +269,11 @@ class ResBlock(nn.Module):
             fold = input.is_cuda and self.skip is not None and self.skip.scalable() and self.conv2.scalable()
             out = self.conv2(self.conv1(input), gain_mul=_INV_SQRT2 if fold else 1.0)
         if fold:        # 1/sqrt(2) lives in conv2's activation gain and the skip's weights: the merge is a plain sum
-            return self.skip(input, residual=out, res_scale=1.0, weight_mul=_INV_SQRT2)
+            return self.skip(block_input, residual=out, res_scale=1.0, weight_mul=_INV_SQRT2, pre_low=low)
         if self.skip is None:
-            return add_scale(out, input, _INV_SQRT2)
-        return self.skip(input, residual=out, res_scale=_INV_SQRT2)      # (out + skip)/sqrt(2) in the skip's epilogue
+            return add_scale(out, block_input, _INV_SQRT2)
+        # (out + skip)/sqrt(2) in the skip's epilogue
+        return self.skip(block_input, residual=out, res_scale=_INV_SQRT2, pre_low=low)
 
 
 class DisentanglementEncoder(nn.Module):

@@ -98,6 +98,39 @@ class UpFirDn2d(Function):
         return gx, None, None, None, None, gres, None
 
 
+class SplitDown(Function):
+    """x -> (x, upfirdn2d(x, kernel, down=2, pad)): the two uses of a down-sampling residual block's input -- its
+    main path and the Blur of its skip path (models.py:213-227) -- as ONE autograd node.  Forward is the fused
+    down-sampling kernel it always was.  The point is the backward: the node receives both gradients at once, so
+    the adjoint of the blur (the fused up-sampling kernel) adds the main path's gradient in its epilogue instead of
+    autograd summing the two in a separate pass over the full-resolution tensor."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, pad):
+        require_cuda(x, kernel)
+        kernel = kernel.contiguous()
+        x = nhwc(x)
+        low = _run(x, kernel, (1, 1), (2, 2), pad)
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        ctx.cfg = (pad, tuple(x.shape), (low.shape[2], low.shape[3]))
+        ctx.set_materialize_grads(False)
+        return x.view_as(x), low
+
+    @staticmethod
+    def backward(ctx, gx, glow):
+        kernel, gkernel = ctx.saved_tensors
+        pad, in_size, out_size = ctx.cfg
+        if glow is None:
+            return gx, None, None
+        g_pad = _grad_pad(in_size[2:], out_size, kernel.shape, (1, 1), (2, 2), pad)
+        if gx is None or torch.is_grad_enabled() or not residual_ok(glow, gkernel, (2, 2), (1, 1)):
+            g = UpFirDn2dBackward.apply(glow, kernel, gkernel, (1, 1), (2, 2), pad, g_pad, in_size, out_size)
+            return (g if gx is None else g + gx), None, None
+        out = _run(nhwc(glow), gkernel, (2, 2), (1, 1), g_pad, residual=nhwc(gx), res_scale=1.0)
+        assert tuple(out.shape) == tuple(in_size), (out.shape, in_size)
+        return out, None, None
+
+
 class BlurBiasAct(Function):
     """out = scale * lrelu(upfirdn2d(x, kernel, pad) + bias[c]) in one kernel (up = down = 1).
     Equivalent to Blur followed by FusedLeakyReLU (stylegan2/model.py:261,375)."""

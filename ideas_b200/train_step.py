@@ -110,7 +110,7 @@ class Trainer:
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
                  prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = False,
-                 concurrent_generator: bool = True, early_generator: bool = True):
+                 concurrent_generator: bool = True, early_generator: bool = False):
         self.args = args
         self.batch_generator = bool(batch_generator)
         self.concurrent_generator = bool(concurrent_generator)
@@ -464,8 +464,8 @@ class Trainer:
         if self.early_generator and self.multi_stream and not r1:
             # The generator-side forward of the next phase reads no discriminator, and E / G / Gstru do not change
             # in this one: start it on its own streams now, under the discriminators' backward pass and optimiser
-            # step.  Same values, same order of random draws (the backward pass draws nothing).  Measured: 295.6 vs
-            # 299.6 ms per step.
+            # step.  Same values, same order of random draws (the backward pass draws nothing).  Measured: no gain
+            # (285.0 vs 284.8 ms per step), so it is off by default.
             for k in EMA_KEYS:
                 requires_grad(t[k], True)
             drawn = generator_draws()

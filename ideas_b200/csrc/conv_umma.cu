@@ -719,6 +719,7 @@ std::atomic<int> g_pmh_mode{1};               // 0 = never, 1 = heuristic, 2 = w
 std::atomic<int> g_pmh_resident{1};           // keep small filters in shared memory for the CTA's lifetime
 std::atomic<int> g_pmh_xstages{2};            // slab ring depth (2 or 3)
 std::atomic<int> g_pmh_minbw{0};              // tile search: smallest tile width considered (0 = no bound)
+std::atomic<int> g_pmh_align{0};              // tile search: padded row width must be a multiple of this (0 = any)
 
 struct alignas(64) PmhParams {
   CUtensorMap src;
@@ -984,7 +985,8 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, int res
   static std::map<Key, PmhTile> cache;
   const int xst = g_pmh_xstages.load() == 3 ? 3 : 2;
   const int minbw = g_pmh_minbw.load();
-  const Key key{QW, QH, hx * 16 + hy, ntaps + 64 * resident_tiles, oct, xst * 1024 + minbw};
+  const int align = g_pmh_align.load();
+  const Key key{QW, QH, hx * 16 + hy, ntaps + 64 * resident_tiles, oct + 4096 * align, xst * 1024 + minbw};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -998,6 +1000,7 @@ bool choose_pmh_tile(int QW, int QH, int hx, int hy, int ntaps, int oct, int res
   if (minbw > bw0) bw0 = minbw < QW ? minbw : QW;
   for (int bw = bw0; bw <= QW && bw + hx <= 256; ++bw) {
     const int bwp = bw + hx;
+    if (align > 1 && bwp % align != 0) continue;
     for (int bh = 1; bh <= QH && bh + hy <= 256; ++bh) {
       const int nsub = ceil_div(bh * bwp, 128);
       if (nsub > max_sub) break;
@@ -1568,6 +1571,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "pmh_xstages")) {
     ideas::g_pmh_xstages.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pmh_align")) {
+    ideas::g_pmh_align.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "pmh_minbw")) {

@@ -296,9 +296,29 @@ class ConvWgrad(Function):
         return g_x, g_dy, None
 
 
-def _blur_act_bwd_ok(channels: int) -> bool:
+def _blur_act_bwd_ok(channels: int, kernel=None, batch: int = 1) -> bool:
+    """Host-side statement of the fast-path envelope of ideas_blur_act_backward / ideas_blur_scale_dot_backward."""
     c4 = channels // 4
-    return channels % 4 == 0 and ((c4 <= 128 and 128 % c4 == 0) or c4 % 128 == 0)
+    if kernel is not None and (kernel.shape[0] > 4 or kernel.shape[1] > 4):
+        return False
+    return channels % 4 == 0 and batch <= 65535 and ((c4 <= 128 and 128 % c4 == 0) or c4 % 128 == 0)
+
+
+def _modconv_act_backward(gy, out, d, alpha, gain, n, p, c):
+    """g1d, gsum, dotz of ideas_modconv_act_backward; composed of torch ops outside the kernel's envelope
+    (channels not a multiple of 4, or more than 2048 of them)."""
+    if c % 4 == 0 and c <= 2048:
+        g1d = torch.empty_like(out)
+        gsum = torch.zeros((n, c), device=out.device, dtype=out.dtype)
+        dotz = torch.zeros_like(gsum)
+        _lib.call("ideas_modconv_act_backward", ptr(g1d), ptr(gsum), ptr(dotz), ptr(gy), ptr(out), ptr(d), float(alpha),
+                  float(gain), n, p, c, stream_ptr(out))
+        return g1d, gsum, dotz
+    slope = torch.where(out > 0, 1.0, float(alpha))
+    g1 = gy * slope * gain
+    z = out / (slope * gain)
+    g1d = g1 if d is None else g1 * d.view(n, c, 1, 1)
+    return g1d, g1.sum(dim=(2, 3)), (g1 * z).sum(dim=(2, 3))
 
 
 class ConvActBlur(Function):
@@ -327,7 +347,7 @@ class ConvActBlur(Function):
         g, alpha, gain, pad4, zhw = ctx.cfg
         want_bias = ctx.needs_input_grad[2]
         g_pad = _grad_pad((y.shape[2], y.shape[3]), zhw, kernel.shape, (1, 1), (1, 1), pad4)
-        if torch.is_grad_enabled() or not _blur_act_bwd_ok(g.K):
+        if torch.is_grad_enabled() or not _blur_act_bwd_ok(g.K, gkernel, g.N):
             gy = UpFirDn2dBackward.apply(gz, kernel, gkernel, (1, 1), (1, 1), pad4, g_pad, tuple(y.shape), zhw)
             g1, gb = FusedLeakyReLUFunctionBackward.apply(gy, y, want_bias, alpha, gain)
             gx = ConvDgrad.apply(g1, wp, g) if ctx.needs_input_grad[0] else None
@@ -432,11 +452,7 @@ def _post_act_backward(gym, out, post, d, bias, alpha, gain, n, p, c):
     gsum = post*gsum', dotz = post*dotz' (bias and demodulation gradients of this layer)."""
     gym = nhwc(gym)
     eff = post if d is None else (post * d).contiguous()
-    g1d = torch.empty_like(out)
-    gsum = torch.zeros((n, c), device=out.device, dtype=out.dtype)
-    dotz = torch.zeros_like(gsum)
-    _lib.call("ideas_modconv_act_backward", ptr(g1d), ptr(gsum), ptr(dotz), ptr(gym), ptr(out), ptr(eff), float(alpha),
-              float(gain), n, p, c, stream_ptr(out))
+    g1d, gsum, dotz = _modconv_act_backward(gym, out, eff, alpha, gain, n, p, c)
     return g1d, post * gsum, post * dotz, dotz
 
 
@@ -524,11 +540,7 @@ class ModConv(Function):
                 gd = (dotz - (bias * gsum if bias is not None else 0.0)) / d
         elif ctx.act:
             gy = nhwc(gy)
-            g1d = torch.empty_like(out)
-            gsum = torch.zeros((g.N, g.K), device=gy.device, dtype=gy.dtype)
-            dotz = torch.zeros_like(gsum)
-            _lib.call("ideas_modconv_act_backward", ptr(g1d), ptr(gsum), ptr(dotz), ptr(gy), ptr(out), ptr(d),
-                      float(ctx.alpha), float(ctx.gain), g.N, P, g.K, st)
+            g1d, gsum, dotz = _modconv_act_backward(gy, out, d, ctx.alpha, ctx.gain, g.N, P, g.K)
             if bias is not None:
                 gb = gsum.sum(0)
             if d is not None:
@@ -655,7 +667,7 @@ class ModConvUp(Function):
                           ctx.blur_pad)
         gkernel = torch.flip(kernel, [0, 1])
         gd = None
-        if d is not None and _blur_act_bwd_ok(g.C) and kernel.shape[0] <= 4 and kernel.shape[1] <= 4 and g.N <= 65535:
+        if d is not None and _blur_act_bwd_ok(g.C, kernel, g.N):
             # blur^T, the demodulation scale and dL/dd = sum_p gu * u / d in ONE kernel: the blurred gradient is
             # never written (was: blur backward, then a channel_dot pass over (u, gu))
             g1 = nhwc(g1)

@@ -11,6 +11,10 @@ from ideas_b200 import _lib
 from ideas_b200._tensor import ptr, stream_ptr
 
 dev = torch.device("cuda")
+if os.environ.get("PMH_PROBE"):
+    # compute-dense, L2-resident shapes: what MMA rate does the pixel-major halo kernel sustain at N = 64 / 32 / 128 ?
+    PROBE = [("forward", 32, 128, 64, 64, 3, 1, 1), ("forward", 32, 128, 32, 64, 3, 1, 1), ("forward", 32, 128, 128, 64, 3, 1, 1),
+             ("forward", 32, 128, 64, 64, 1, 1, 0), ("forward", 32, 32, 64, 258, 3, 1, 0)]
 CASES = [
     # kind, N, C, K, H, k, stride, pad
     ("forward", 32, 32, 64, 258, 3, 1, 0), ("dgrad", 32, 32, 64, 258, 3, 1, 0),
@@ -24,6 +28,8 @@ CASES = [
     ("forward", 32, 128, 256, 16, 3, 1, 1), ("dgrad", 32, 128, 256, 16, 3, 1, 1), ("forward", 96, 512, 512, 16, 3, 1, 1),
 ]
 iters = int(os.environ.get("ITERS", "5"))
+if os.environ.get("PMH_PROBE"):
+    CASES = PROBE
 print(f"{'kind':8s} {'N':>5s} {'C':>4s} {'K':>4s} {'H':>4s} k s p | pmh=0 ms  TF/s | pmh=2 ms  TF/s | speed-up")
 for kind, N, C, K, H, k, s, pad in CASES:
     OH = (H + 2 * pad - k) // s + 1

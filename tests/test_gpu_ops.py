@@ -594,3 +594,53 @@ def test_styled_conv_pair_with_premodulation(conv_mode, up):
     ref = torch.autograd.grad((c2(c1(x, st), st) * gy).sum() + (c1(x, st) ** 2).sum(), params)
     for g_, w_ in zip(both, ref):
         assert T.rel(g_, w_) <= 5 * tol
+
+
+def test_split_down_matches_separate_ops():
+    """SplitDown (op/upfirdn2d.py): (x, blur_down2(x)) as one node whose backward adds the two gradients inside the
+    blur's adjoint kernel, against the two separate uses of x that autograd would sum."""
+    from ideas_b200.stylegan2.model import make_kernel
+    from ideas_b200.stylegan2.op.upfirdn2d import SplitDown, upfirdn2d
+    g = torch.Generator().manual_seed(6)
+    k = make_kernel([1, 3, 3, 1]).cuda()
+    for shape, pad in (((2, 8, 16, 16), (1, 1)), ((3, 64, 33, 21), (1, 1)), ((2, 12, 9, 10), (2, 1))):
+        x = torch.randn(*shape, generator=g).cuda().requires_grad_(True)
+        xa, low = SplitDown.apply(x, k, (pad[0], pad[1], pad[0], pad[1]))
+        want_low = upfirdn2d(x, k, down=2, pad=pad)
+        assert rel(low, want_low) <= 1e-6 and torch.equal(xa, x)
+        g_main = torch.randn(*shape, generator=g).cuda()
+        g_low = torch.randn(*low.shape, generator=g).cuda()
+        (got,) = torch.autograd.grad([xa, low], [x], [g_main, g_low])
+        (want,) = torch.autograd.grad([x * 1.0, want_low], [x], [g_main, g_low])
+        assert rel(got, want) <= 1e-6, shape
+        # only one of the two outputs used
+        xa, low = SplitDown.apply(x, k, (pad[0], pad[1], pad[0], pad[1]))
+        (g1,) = torch.autograd.grad(low, [x], g_low)
+        (w1,) = torch.autograd.grad(upfirdn2d(x, k, down=2, pad=pad), [x], g_low)
+        assert rel(g1, w1) <= 1e-6
+
+
+@pytest.mark.parametrize("down", [False, True])
+def test_resblock_scale_folding_matches_unfused(conv_mode, down):
+    """ResBlock with (out + skip)/sqrt(2) folded into conv2's activation gain and the skip convolution's weights (and,
+    for down-sampling blocks, SplitDown at the input) against the same block evaluated layer by layer with an explicit
+    add_scale merge: output and every gradient."""
+    import math
+    from ideas_b200.models import ResBlock
+    from ideas_b200.stylegan2.op.elementwise import add_scale
+    torch.manual_seed(5)
+    blk = ResBlock(32, 64, downsample=down).cuda()
+    for p in blk.parameters():
+        if p.dim() == 1:
+            p.data.normal_()
+    x = torch.randn(2, 32, 20, 20).cuda().requires_grad_(True)
+    params = [x] + list(blk.parameters())
+    got = blk(x)
+    plain = add_scale(blk.conv2(blk.conv1(x)), blk.skip(x), 1 / math.sqrt(2))
+    gy = torch.randn_like(plain)
+    gg = torch.autograd.grad(got, params, gy)
+    wg = torch.autograd.grad(plain, params, gy)
+    tol = 2e-5 if conv_mode == "fp32" else 1e-3
+    assert T.rel(got, plain) <= tol
+    for a, b, p in zip(gg, wg, params):
+        assert T.rel(a, b) <= 5 * tol, tuple(p.shape)

@@ -350,6 +350,8 @@ constexpr int kHaloEpiWarps = 8;
 constexpr uint32_t kHaloWBytes = 128 * 128;   // 128 output channels x 32 fp32 input channels
 constexpr int kHaloSlack = 24;                // rows past the box that rounding N up to 16 may touch
 constexpr uint32_t kHaloSmemBudget = 224 * 1024;
+constexpr uint32_t kHaloStageBytes = kHaloEpiWarps * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
+std::atomic<int> g_halo_epi{1};               // option "halo_epi": 1 = transposed 128-bit-store epilogue, 0 = per-element stores
 
 std::atomic<int> g_halo_mode{1};              // 0 = never, 1 = heuristic, 2 = whenever eligible
 
@@ -375,6 +377,7 @@ struct alignas(64) HaloParams {
   int x_stages, w_stages;
   uint32_t x_slot_bytes, x_tx_bytes;
   int act;
+  int epi;
   float alpha, gain;
   TapH taps[kMaxTaps];
 };
@@ -535,6 +538,52 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
       ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      if (p.epi) {
+        // Transposed epilogue: tcgen05.ld hands a thread (= one output channel) 32 consecutive pixels.  The thread
+        // finishes them (demodulation, bias, leaky ReLU: per-channel scalars), writes them as one COLUMN of a private
+        // 32 pixel x 32 channel shared-memory tile (a warp store = one 128-byte row segment, conflict-free), and the
+        // tile comes back row-wise: lane l owns the 16-byte chunk l%8 of pixels l/8 + 4j, so one global store
+        // instruction writes four complete 128-byte lines instead of 32 four-byte pieces, and the pixel -> address
+        // arithmetic runs once per pixel group instead of once per element.
+        const uint32_t stage = xring + p.x_stages * p.x_slot_bytes + (uint32_t)(warp - 3) * 4096u;
+        const int cj = lane & 7, pr = lane >> 3;
+        const int kc = k0 + quarter * 32 + cj * 4;               // first of this lane's four channels on the way out
+        const bool kcok = kc < p.OC;
+        const int units = (npix + 31) >> 5;
+        const int64_t rowwrap = (int64_t)row_step - (int64_t)p.bwp * pix_step;
+        float* const obase = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + kc;
+        for (int u = half; u < units; u += 2) {
+          float v[32];
+          ptx::tmem_ld_32x32(acc + (uint32_t)(u << 5), v);
+          __syncwarp();                                   // the previous unit's reads of the tile are done
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float r = fmaf(v[j], os, bs);
+            r = (lrelu_on && r < 0.f) ? r * alpha : r;
+            r *= gain;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (uint32_t)(j * 128 + lane * 4)), "f"(r) : "memory");
+          }
+          __syncwarp();
+          const int m = (u << 5) + pr;
+          int y = m / p.bwp;
+          int x = m - y * p.bwp;
+          float* op = obase + (int64_t)y * row_step + (int64_t)x * pix_step;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 r;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                         : "r"(stage + (uint32_t)((4 * j + pr) * 128 + cj * 16)));
+            if (kcok && x < xlim && y < ylim) *reinterpret_cast<float4*>(op) = r;
+            x += 4;
+            op += 4 * pix_step;
+            if (x >= p.bwp) { x -= p.bwp; ++y; op += rowwrap; }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ptx::smem_u32(&tempty[buf]));
+        continue;
+      }
       for (int c = half; c < chunks; c += 2) {
         const int m0 = c << 4;
         const int y0 = m0 / p.bwp;
@@ -598,7 +647,7 @@ bool choose_halo_tile(int QW, int QH, int hx, int hy, int ntaps, HaloTile* out) 
       const int nmma = ((bh * bwp + 15) / 16) * 16;
       const int rows = bh + hy;
       const uint32_t slot = (uint32_t)((rows * bwp + hx + kHaloSlack) * 128 + 1023) & ~1023u;
-      if (2 * slot + 4 * kHaloWBytes > kHaloSmemBudget) break;
+      if (2 * slot + 4 * kHaloWBytes + kHaloStageBytes > kHaloSmemBudget) break;
       const int tx = ceil_div(QW, bw), ty = ceil_div(QH, bh);
       const double mma = (double)ntaps * 4 * (nmma / 2.0);
       const double l2 = ((double)ntaps * kHaloWBytes + (double)rows * bwp * 128) / 48.0;
@@ -606,7 +655,7 @@ bool choose_halo_tile(int QW, int QH, int hx, int hy, int ntaps, HaloTile* out) 
       if (cyc < best.cycles) {
         best.bw = bw; best.bwp = bwp; best.bh = bh; best.nmma = nmma; best.tiles_x = tx; best.tiles_y = ty;
         best.slot_bytes = slot; best.cycles = cyc; best.x_stages = 2;
-        const int ws = (int)((kHaloSmemBudget - 2 * slot) / kHaloWBytes);
+        const int ws = (int)((kHaloSmemBudget - kHaloStageBytes - 2 * slot) / kHaloWBytes);
         best.w_stages = ws > kHaloMaxWStages ? kHaloMaxWStages : ws;
       }
     }
@@ -679,7 +728,8 @@ int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
     int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
     if (rc) return rc;
   }
-  const uint32_t smem = p.w_stages * kHaloWBytes + p.x_stages * p.x_slot_bytes + 1024;
+  const uint32_t smem = p.w_stages * kHaloWBytes + p.x_stages * p.x_slot_bytes + kHaloStageBytes + 1024;
+  p.epi = g_halo_epi.load();
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -1555,6 +1605,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "halo")) {
     ideas::g_halo_mode.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "halo_epi")) {
+    ideas::g_halo_epi.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "tail_split")) {

@@ -16,6 +16,9 @@
 namespace ideas {
 
 // implemented in conv_umma.cu; return IDEAS_ERR_UNSUPPORTED when the shape does not qualify
+int umma_dgrad_phases_launch(const ConvGeom* gs, int nph, float* dst, const float* src, const float* w,
+                             const float* out_scale, const float* bias, int act, float alpha, float gain,
+                             cudaStream_t st);
 int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
                      const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run,
                      const float* residual = nullptr, float res_scale = 1.f);
@@ -457,6 +460,21 @@ extern "C" int ideas_conv2d_dgrad(float* dx, const float* dy, const float* wpt, 
   if (N == 0) return IDEAS_OK;
   IDEAS_REQUIRE(dx && dy && wpt, "conv2d_dgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (stride == 2 && umma_wanted(impl) && !out_scale && H >= 2 && W >= 2) {
+    ConvGeom gs[4];
+    int nph = 0;
+    bool ok = true;
+    for (int py = 0; py < 2 && ok; ++py)
+      for (int px = 0; px < 2 && ok; ++px) {
+        gs[nph] = geom_dgrad_phase(N, H, W, C, K, kh, kw, stride, pad, OH, OW, py, px);
+        ok = gs[nph].ntaps >= 1;      // a phase without taps is bias/zero only: leave it to the per-phase path
+        ++nph;
+      }
+    if (ok) {
+      rc = umma_dgrad_phases_launch(gs, nph, dx, dy, wpt, in_scale, bias, act, alpha, gain, st);
+      if (rc != IDEAS_ERR_UNSUPPORTED) return rc;
+    }
+  }
   for (int py = 0; py < stride; ++py)
     for (int px = 0; px < stride; ++px) {
       if (py >= H || px >= W) continue;

@@ -351,6 +351,7 @@ constexpr uint32_t kHaloWBytes = 128 * 128;   // 128 output channels x 32 fp32 i
 constexpr int kHaloSlack = 24;                // rows past the box that rounding N up to 16 may touch
 constexpr uint32_t kHaloSmemBudget = 224 * 1024;
 constexpr uint32_t kHaloStageBytes = kHaloEpiWarps * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
+std::atomic<int> g_dgrad_phases{1};          // option "dgrad_phases": strided data gradients: all phases in one halo launch
 std::atomic<int> g_halo_epi{1};               // option "halo_epi": 1 = transposed 128-bit-store epilogue, 0 = per-element stores
 
 std::atomic<int> g_halo_mode{1};              // 0 = never, 1 = heuristic, 2 = whenever eligible
@@ -379,6 +380,12 @@ struct alignas(64) HaloParams {
   int act;
   int epi;
   float alpha, gain;
+  // Output phases served by ONE launch (nphase > 1: the stride^2 phases of a strided data gradient / transposed conv).
+  // Every phase reads the same source tensor, so running the phases of a pixel tile on neighbouring CTAs at the same
+  // time turns three of the four reads of each activation slab into L2 hits (separate launches re-read the whole
+  // tensor from HBM once per phase: it is several times the size of the L2).  ph[0] mirrors the scalar fields above.
+  int nphase;
+  struct Phase { int ntaps, tap0, o_py, o_px, QH, QW, x_org, y_org; } ph[4];
   TapH taps[kMaxTaps];
 };
 
@@ -431,14 +438,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
   const uint32_t tmem_base = tmem_slot;
 
   // item -> (k-tile, pixel tile); the k-tile runs fastest so that concurrently running CTAs share activations
-#define IDEAS_HALO_DECODE(item)                         \
-  const int kt = (item) % p.ktiles;                     \
-  const int pt = (item) / p.ktiles;                     \
-  const int bx = pt % p.tiles_x;                        \
-  const int tt = pt / p.tiles_x;                        \
-  const int qx0 = bx * p.bw;                            \
-  const int qy0 = (tt % p.tiles_y) * p.bh;              \
-  const int n = tt / p.tiles_y;                         \
+  // item -> (phase, k-tile, pixel tile).  The nphase items of a (k-tile, pixel tile) are consecutive, i.e. run on
+  // neighbouring CTAs in the same round; the phase is rotated by the round so that every CTA sees all phases in turn
+  // (they differ in cost: 1, 2, 2 and 4 taps for a 3x3 stride-2 filter).  gridDim.x is a multiple of nphase.
+#define IDEAS_HALO_DECODE(item)                                                       \
+  const int phs = ((item) % p.nphase + (item) / (int)gridDim.x) % p.nphase;           \
+  const int tix = (item) / p.nphase;                                                  \
+  const int kt = tix % p.ktiles;                                                      \
+  const int pt = tix / p.ktiles;                                                      \
+  const int bx = pt % p.tiles_x;                                                      \
+  const int tt = pt / p.tiles_x;                                                      \
+  const int qx0 = bx * p.bw;                                                          \
+  const int qy0 = (tt % p.tiles_y) * p.bh;                                            \
+  const int n = tt / p.tiles_y;                                                       \
   const int k0 = kt * 128;
 
   if (warp == 0) {
@@ -448,13 +460,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        const int k0 = (item % p.ktiles) * 128;
+        IDEAS_HALO_DECODE(item)
+        (void)qx0; (void)qy0; (void)n;
+        const int nt = p.ph[phs].ntaps, t0 = p.ph[phs].tap0;
         for (int cs = 0; cs < p.csteps; ++cs)
-          for (int t = 0; t < p.ntaps; ++t) {
+          for (int t = 0; t < nt; ++t) {
             ptx::mbar_wait(ptx::smem_u32(&wempty[stage]), phase ^ 1u);
             const uint32_t fb = ptx::smem_u32(&wfull[stage]);
             ptx::mbar_arrive_expect_tx(fb, kHaloWBytes);
-            ptx::tma_load_3d(wring + stage * kHaloWBytes, &p.w, fb, cs * kBlockK, k0, p.taps[t].widx);
+            ptx::tma_load_3d(wring + stage * kHaloWBytes, &p.w, fb, cs * kBlockK, k0, p.taps[t0 + t].widx);
             if (++stage == p.w_stages) { stage = 0; phase ^= 1u; }
           }
       }
@@ -472,7 +486,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
           ptx::mbar_wait(ptx::smem_u32(&xempty[stage]), phase ^ 1u);
           const uint32_t fb = ptx::smem_u32(&xfull[stage]);
           ptx::mbar_arrive_expect_tx(fb, p.x_tx_bytes);
-          ptx::tma_load_4d(xring + stage * p.x_slot_bytes, &p.src, fb, cs * kBlockK, qx0 + p.x_org, qy0 + p.y_org, n);
+          ptx::tma_load_4d(xring + stage * p.x_slot_bytes, &p.src, fb, cs * kBlockK, qx0 + p.ph[phs].x_org,
+                           qy0 + p.ph[phs].y_org, n);
           if (++stage == p.x_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -486,17 +501,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
       int it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int buf = it & 1;
+        const int phs = (item % p.nphase + item / (int)gridDim.x) % p.nphase;
+        const int nt = p.ph[phs].ntaps, t0 = p.ph[phs].tap0;
         ptx::mbar_wait(ptx::smem_u32(&tempty[buf]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem_base + buf * 256;
         for (int cs = 0; cs < p.csteps; ++cs) {
           ptx::mbar_wait(ptx::smem_u32(&xfull[xs]), xphase);
           const uint32_t xa = xring + xs * p.x_slot_bytes;
-          for (int t = 0; t < p.ntaps; ++t) {
+          for (int t = 0; t < nt; ++t) {
             ptx::mbar_wait(ptx::smem_u32(&wfull[ws]), wphase);
             ptx::tc_fence_after();
             const uint64_t adesc = ptx::smem_desc_sw128(wring + ws * kHaloWBytes, 16, 1024);
-            const uint64_t bdesc = ptx::smem_desc_sw128(xa + (uint32_t)p.taps[t].rowoff * 128u, 16, 1024);
+            const uint64_t bdesc = ptx::smem_desc_sw128(xa + (uint32_t)p.taps[t0 + t].rowoff * 128u, 16, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               ptx::mma_tf32(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cs | t | k) != 0));
@@ -532,9 +549,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
         if (p.out_scale) os = __ldg(p.out_scale + (int64_t)n * p.OC + k);
         if (p.bias) bs = __ldg(p.bias + k);
       }
-      const int xlim = min(p.bw, p.QW - qx0);
-      const int ylim = min(p.bh, p.QH - qy0);
-      float* base = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + k;
+      const int o_py = p.ph[phs].o_py, o_px = p.ph[phs].o_px;
+      const int xlim = min(p.bw, p.ph[phs].QW - qx0);
+      const int ylim = min(p.bh, p.ph[phs].QH - qy0);
+      float* base = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + o_py)) * p.OW + ((int64_t)qx0 * p.o_s + o_px)) * p.OC + k;
       ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
@@ -551,7 +569,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
         const bool kcok = kc < p.OC;
         const int units = (npix + 31) >> 5;
         const int64_t rowwrap = (int64_t)row_step - (int64_t)p.bwp * pix_step;
-        float* const obase = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + p.o_py)) * p.OW + ((int64_t)qx0 * p.o_s + p.o_px)) * p.OC + kc;
+        float* const obase = p.dst + (((int64_t)n * p.OH + ((int64_t)qy0 * p.o_s + o_py)) * p.OW + ((int64_t)qx0 * p.o_s + o_px)) * p.OC + kc;
         for (int u = half; u < units; u += 2) {
           float v[32];
           ptx::tmem_ld_32x32(acc + (uint32_t)(u << 5), v);
@@ -668,21 +686,40 @@ bool choose_halo_tile(int QW, int QH, int hx, int hy, int ntaps, HaloTile* out) 
   return best.bw > 0;
 }
 
-int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
-                     const float* bias, int act, float alpha, float gain, cudaStream_t st) {
+// nph == 1: one geometry.  nph > 1: the output phases of one strided data gradient (same tensors, same channel
+// counts; each phase has its own taps, q grid and destination offset), served by a single launch.
+int halo_conv_launch_phases(const ConvGeom* gs, int nph, float* dst, const float* src, const float* w,
+                            const float* out_scale, const float* bias, int act, float alpha, float gain,
+                            cudaStream_t st) {
   const int mode = g_halo_mode.load();
-  if (mode == 0 || g.i_s != 1 || g.ntaps < 2) return IDEAS_ERR_UNSUPPORTED;
-  if (g.QW < 8 || g.QH < 1) return IDEAS_ERR_UNSUPPORTED;
-  int min_dx = 1 << 30, max_dx = -(1 << 30), min_dy = 1 << 30, max_dy = -(1 << 30), max_widx = 0;
-  for (int t = 0; t < g.ntaps; ++t) {
-    min_dx = g.taps[t].dx < min_dx ? g.taps[t].dx : min_dx; max_dx = g.taps[t].dx > max_dx ? g.taps[t].dx : max_dx;
-    min_dy = g.taps[t].dy < min_dy ? g.taps[t].dy : min_dy; max_dy = g.taps[t].dy > max_dy ? g.taps[t].dy : max_dy;
-    max_widx = g.taps[t].widx > max_widx ? g.taps[t].widx : max_widx;
+  const ConvGeom& g = gs[0];
+  if (mode == 0 || nph < 1 || nph > 4) return IDEAS_ERR_UNSUPPORTED;
+  if (nph == 1 && g.ntaps < 2) return IDEAS_ERR_UNSUPPORTED;
+  int hx = 0, hy = 0, max_widx = 0, QWm = 0, QHm = 0, total_taps = 0, max_taps = 0;
+  int min_dx[4], min_dy[4];
+  for (int f = 0; f < nph; ++f) {
+    const ConvGeom& q = gs[f];
+    if (q.i_s != 1 || q.ntaps < 1 || q.QW < 1 || q.QH < 1) return IDEAS_ERR_UNSUPPORTED;
+    if (q.N != g.N || q.IC != g.IC || q.OC != g.OC || q.IH != g.IH || q.IW != g.IW || q.OH != g.OH ||
+        q.OW != g.OW || q.o_s != g.o_s)
+      return IDEAS_ERR_UNSUPPORTED;
+    int lo_x = 1 << 30, hi_x = -(1 << 30), lo_y = 1 << 30, hi_y = -(1 << 30);
+    for (int t = 0; t < q.ntaps; ++t) {
+      lo_x = q.taps[t].dx < lo_x ? q.taps[t].dx : lo_x; hi_x = q.taps[t].dx > hi_x ? q.taps[t].dx : hi_x;
+      lo_y = q.taps[t].dy < lo_y ? q.taps[t].dy : lo_y; hi_y = q.taps[t].dy > hi_y ? q.taps[t].dy : hi_y;
+      max_widx = q.taps[t].widx > max_widx ? q.taps[t].widx : max_widx;
+    }
+    min_dx[f] = lo_x; min_dy[f] = lo_y;
+    hx = hi_x - lo_x > hx ? hi_x - lo_x : hx;
+    hy = hi_y - lo_y > hy ? hi_y - lo_y : hy;
+    QWm = q.QW > QWm ? q.QW : QWm; QHm = q.QH > QHm ? q.QH : QHm;
+    total_taps += q.ntaps;
+    max_taps = q.ntaps > max_taps ? q.ntaps : max_taps;
   }
-  const int hx = max_dx - min_dx, hy = max_dy - min_dy;
+  if (QWm < 8 || total_taps > kMaxTaps) return IDEAS_ERR_UNSUPPORTED;
   if (hx > 8 || hy > 8) return IDEAS_ERR_UNSUPPORTED;
   HaloTile tile;
-  if (!choose_halo_tile(g.QW, g.QH, hx, hy, g.ntaps, &tile)) return IDEAS_ERR_UNSUPPORTED;
+  if (!choose_halo_tile(QWm, QHm, hx, hy, max_taps, &tile)) return IDEAS_ERR_UNSUPPORTED;
   if (mode == 1) {
     // heuristic from scripts/kernels_microbench.py (IDEAS_HALO=0 vs 2): with <= 128 input channels the
     // pixel-major kernel is bound by activation re-reads and by its exposed epilogue (halo kernel 1.2-1.7x);
@@ -694,14 +731,14 @@ int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
 
   HaloParams p;
   p.dst = dst; p.out_scale = out_scale; p.bias = bias;
-  p.N = g.N; p.QH = g.QH; p.QW = g.QW; p.OH = g.OH; p.OW = g.OW; p.OC = g.OC;
+  p.N = g.N; p.QH = QHm; p.QW = QWm; p.OH = g.OH; p.OW = g.OW; p.OC = g.OC;
   p.o_s = g.o_s; p.o_py = g.o_py; p.o_px = g.o_px;
   p.bw = tile.bw; p.bwp = tile.bwp; p.bh = tile.bh; p.nmma = tile.nmma;
   p.box_rows = tile.bh + hy;
-  p.x_org = min_dx; p.y_org = min_dy;
+  p.x_org = min_dx[0]; p.y_org = min_dy[0];
   p.tiles_x = tile.tiles_x; p.tiles_y = tile.tiles_y;
   p.ktiles = ceil_div(g.OC, 128);
-  const int64_t items = (int64_t)g.N * p.tiles_y * p.tiles_x * p.ktiles;
+  const int64_t items = (int64_t)g.N * p.tiles_y * p.tiles_x * p.ktiles * nph;
   if (items > (1ll << 30)) return IDEAS_ERR_UNSUPPORTED;
   p.items = (int)items;
   p.ntaps = g.ntaps; p.csteps = g.IC / kBlockK;
@@ -710,9 +747,20 @@ int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
   p.x_slot_bytes = tile.slot_bytes;
   p.x_tx_bytes = (uint32_t)(p.box_rows * p.bwp * 128);
   p.act = act; p.alpha = alpha; p.gain = gain;
-  for (int t = 0; t < g.ntaps; ++t) {
-    p.taps[t].rowoff = (g.taps[t].dy - min_dy) * p.bwp + (g.taps[t].dx - min_dx);
-    p.taps[t].widx = g.taps[t].widx;
+  p.nphase = nph;
+  int tap0 = 0;
+  for (int f = 0; f < 4; ++f) {
+    const ConvGeom& q = gs[f < nph ? f : 0];
+    const int ff = f < nph ? f : 0;
+    p.ph[f].ntaps = q.ntaps; p.ph[f].tap0 = f < nph ? tap0 : 0;
+    p.ph[f].o_py = q.o_py; p.ph[f].o_px = q.o_px; p.ph[f].QH = q.QH; p.ph[f].QW = q.QW;
+    p.ph[f].x_org = min_dx[ff]; p.ph[f].y_org = min_dy[ff];
+    if (f >= nph) continue;
+    for (int t = 0; t < q.ntaps; ++t) {
+      p.taps[tap0 + t].rowoff = (q.taps[t].dy - min_dy[f]) * p.bwp + (q.taps[t].dx - min_dx[f]);
+      p.taps[tap0 + t].widx = q.taps[t].widx;
+    }
+    tap0 += q.ntaps;
   }
   {
     const uint64_t dims[4] = {(uint64_t)g.IC, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
@@ -737,10 +785,16 @@ int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
                                     kHaloSmemBudget + 1024);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_halo: cudaFuncSetAttribute");
-  const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  int grid = p.items < kNumSMs ? p.items : kNumSMs;
+  grid -= grid % nph;            // the phase rotation in the kernel needs a whole number of phase groups per round
   conv_umma_halo_kernel<<<grid, kHaloThreads, smem, st>>>(p);
   IDEAS_CHECK_LAUNCH("conv_umma_halo");
   return IDEAS_OK;
+}
+
+int halo_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
+                     const float* bias, int act, float alpha, float gain, cudaStream_t st) {
+  return halo_conv_launch_phases(&g, 1, dst, src, w, out_scale, bias, act, alpha, gain, st);
 }
 
 
@@ -1122,7 +1176,6 @@ int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float
   p.x_stages = tile.x_stages;
   p.w_stages = tile.w_stages;
   p.w_resident = resident ? 1 : 0;
-  p.w_resident = resident ? 1 : 0;
   p.x_slot_bytes = tile.slot_bytes;
   p.x_tx_bytes = (uint32_t)(p.box_rows * p.bwp * 128);
   p.w_bytes = (uint32_t)oct * 128u;
@@ -1160,6 +1213,27 @@ int pmh_conv_launch(const ConvGeom& g, float* dst, const float* src, const float
 }
 
 }  // namespace
+
+// All output phases of a strided data gradient in one launch of the channel-major halo kernel (option
+// "dgrad_phases"): every phase reads the whole dy tensor, and one launch schedules the phases of a pixel tile next
+// to each other so the re-reads hit L2.  IDEAS_ERR_UNSUPPORTED = caller falls back to one launch per phase.
+int umma_dgrad_phases_launch(const ConvGeom* gs, int nph, float* dst, const float* src, const float* w,
+                             const float* out_scale, const float* bias, int act, float alpha, float gain,
+                             cudaStream_t st) {
+  const int mode = g_dgrad_phases.load();
+  if (mode == 0 || nph < 2 || nph > 4) return IDEAS_ERR_UNSUPPORTED;
+  const ConvGeom& g = gs[0];
+  if (g.IC % 32 || g.OC % 32) return IDEAS_ERR_UNSUPPORTED;
+  for (int f = 0; f < nph; ++f)
+    if (gs[f].ntaps < 1 || (int64_t)gs[f].N * gs[f].QH * gs[f].QW < 256 || gs[f].QW < 2) return IDEAS_ERR_UNSUPPORTED;
+  if (!aligned16(dst) || !aligned16(src) || !aligned16(w) || (out_scale && !aligned16(out_scale)) ||
+      (bias && !aligned16(bias)))
+    return IDEAS_ERR_UNSUPPORTED;
+  if (g.IH > 32767 || g.IW > 32767) return IDEAS_ERR_UNSUPPORTED;
+  if (mode == 1 && g_pmh_mode.load() != 0 && !(g.OC % 128 == 0 || g.IC > 128))
+    return IDEAS_ERR_UNSUPPORTED;     // narrow outputs: the pixel-major halo kernel serves the phases one by one
+  return halo_conv_launch_phases(gs, nph, dst, src, w, out_scale, bias, act, alpha, gain, st);
+}
 
 int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const float* w, const float* out_scale,
                      const float* bias, int act, float alpha, float gain, cudaStream_t st, bool dry_run,
@@ -1605,6 +1679,11 @@ extern "C" int ideas_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "halo")) {
     ideas::g_halo_mode.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "dgrad_phases")) {
+    if (value < 0 || value > 2) { ideas::set_error("ideas_set_option: dgrad_phases must be 0, 1 or 2"); return IDEAS_ERR_INVALID; }
+    ideas::g_dgrad_phases.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "halo_epi")) {

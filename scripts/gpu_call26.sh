@@ -1,0 +1,10 @@
+#!/bin/bash
+timeout 900 python -m pytest tests/test_gpu_umma.py -m gpu -q -x 2>&1 | tail -5
+timeout 300 python scripts/bench_dgrad_phases.py 2>&1 | tail -12
+B="python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-library-baseline --no-roofline --no-e2e"
+for cfg in "default::" "phases0:IDEAS_OPTS=dgrad_phases=0:" "phases2:IDEAS_OPTS=dgrad_phases=2:"; do
+  name=${cfg%%:*}; rest=${cfg#*:}; envs=${rest%%:*}; flags=${rest#*:}
+  env $envs timeout 600 $B $flags 2> gpurun_out/r2_ab26_$name.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$name', round(d['ms_per_step'],2), 'ms', d['gpu_launches'], 'launches', d['clocks']['sm_mhz'])"
+done

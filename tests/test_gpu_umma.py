@@ -239,6 +239,37 @@ def test_halo_dgrad_matches_simt(case):
     assert rel(got, ref) <= 1e-3, rel(got, ref)
 
 
+PHASED_DGRAD_CASES = [c for c in DGRAD_CASES if c[6] == 2 and c[5] == 3] + [
+    (2, 128, 256, 67, 65, 3, 2, 0),        # odd, non-square: the four phase grids differ in both directions
+    (1, 64, 128, 130, 130, 3, 2, 1),       # padded stride-2 conv
+    (2, 512, 512, 33, 33, 3, 2, 0),
+    (3, 128, 128, 20, 36, 4, 2, 1),        # 4x4 filter: four taps in every phase
+    (16, 128, 256, 17, 17, 3, 2, 0),       # more items than CTAs: the phase rotation over rounds
+]
+
+
+@pytest.mark.parametrize("case", PHASED_DGRAD_CASES)
+def test_phased_dgrad_single_launch_matches_per_phase(case):
+    """Option dgrad_phases: the stride^2 output phases of a strided data gradient in ONE halo launch (phase-
+    interleaved items) give the same result as one launch per phase, and as the FFMA kernel."""
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(16)
+    dy = torch.randn(N, OH, OW, K, device="cuda", generator=g)
+    wpt = torch.randn(k * k, C, K, device="cuda", generator=g) / (K * k * k) ** 0.5
+    s = torch.rand(N, C, device="cuda", generator=g) + 0.5
+    ref = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_SIMT, s)
+    with _opt(b"dgrad_phases", 0, 1), _halo(2), _opt(b"pmh", 0, 1):
+        per_phase = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_AUTO, s)
+    with _opt(b"dgrad_phases", 2, 1), _halo(2):
+        got = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_AUTO, s)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+    assert rel(got, per_phase) <= 2e-5, rel(got, per_phase)
+
+
 def test_tf32_error_level_vs_fp64():
     """The tensor path multiplies in TF32 (10-bit mantissa) and accumulates in fp32: report and bound
     its error against an fp64 convolution at the cfg-3 reduction length (K = 9 * 512)."""

@@ -80,6 +80,56 @@ template <int BN> struct FwdCfg {
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
 };
 
+// Epilogue of one 128-pixel sub-tile (accumulator columns [j*BN, (j+1)*BN)): one thread = one pixel (TMEM lane),
+// tcgen05.ld of 32 channels at a time -> demodulation -> +bias -> leaky ReLU*gain -> (+residual)*res_scale -> 128-bit
+// NHWC stores.  Shared by the single-CTA and the CTA-pair kernel.
+template <int BN>
+__device__ __forceinline__ void fwd_epilogue_subtile(const FwdParams& p, uint32_t tmem_base, int quarter, int lane, int j,
+                                                     int qx0, int qy0, int n0, bool sub_ok, int k0) {
+  const int row = quarter * 32 + lane;
+  const int wq = row % p.bw;
+  const int t = row / p.bw;
+  const int qx = qx0 + wq, qy = qy0 + (t % p.bh), n = n0 + t / p.bh;
+  const bool valid = sub_ok && n < p.N && qy < p.QH && qx < p.QW;
+  float* dp = nullptr;
+  const float* os = nullptr;
+  const float* rp = nullptr;
+  if (valid) {
+    const int64_t off = (((int64_t)n * p.OH + (qy * p.o_s + p.o_py)) * p.OW + (qx * p.o_s + p.o_px)) * p.OC + k0;
+    dp = p.dst + off;
+    if (p.residual) rp = p.residual + off;
+    if (p.out_scale) os = p.out_scale + (int64_t)n * p.OC + k0;
+  }
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    float v[32];
+    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + ch * 32), v);
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        if (os) {
+          const float4 s = __ldg(reinterpret_cast<const float4*>(os + ch * 32 + i));
+          r.x *= s.x; r.y *= s.y; r.z *= s.z; r.w *= s.w;
+        }
+        if (p.bias) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + i));
+          r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+        }
+        if (p.act == IDEAS_ACT_LRELU) {
+          r.x = lrelu(r.x, p.alpha) * p.gain; r.y = lrelu(r.y, p.alpha) * p.gain;
+          r.z = lrelu(r.z, p.alpha) * p.gain; r.w = lrelu(r.w, p.alpha) * p.gain;
+        }
+        if (rp) {
+          const float4 q = ld_stream4(rp + ch * 32 + i);
+          const float rs = p.res_scale;
+          r.x = (r.x + q.x) * rs; r.y = (r.y + q.y) * rs; r.z = (r.z + q.z) * rs; r.w = (r.w + q.w) * rs;
+        }
+        *reinterpret_cast<float4*>(dp + ch * 32 + i) = r;
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid_constant__ FwdParams p) {
   using Cfg = FwdCfg<BN>;
@@ -173,53 +223,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
     ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
     ptx::tc_fence_after();
 #pragma unroll
     for (int j = 0; j < kSub; ++j) {
       if (j >= nsub) break;
-      const int wq = row % p.bw;
-      const int t = row / p.bw;
-      const int qx = qx0[j] + wq, qy = qy0[j] + (t % p.bh), n = n0[j] + t / p.bh;
-      const bool valid = sub_ok[j] && n < p.N && qy < p.QH && qx < p.QW;
-      float* dp = nullptr;
-      const float* os = nullptr;
-      const float* rp = nullptr;
-      if (valid) {
-        const int64_t off = (((int64_t)n * p.OH + (qy * p.o_s + p.o_py)) * p.OW + (qx * p.o_s + p.o_px)) * p.OC + k0;
-        dp = p.dst + off;
-        if (p.residual) rp = p.residual + off;
-        if (p.out_scale) os = p.out_scale + (int64_t)n * p.OC + k0;
-      }
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        float v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * BN + ch * 32), v);
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            if (os) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(os + ch * 32 + i));
-              r.x *= s.x; r.y *= s.y; r.z *= s.z; r.w *= s.w;
-            }
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + i));
-              r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
-            }
-            if (p.act == IDEAS_ACT_LRELU) {
-              r.x = lrelu(r.x, p.alpha) * p.gain; r.y = lrelu(r.y, p.alpha) * p.gain;
-              r.z = lrelu(r.z, p.alpha) * p.gain; r.w = lrelu(r.w, p.alpha) * p.gain;
-            }
-            if (rp) {
-              const float4 q = ld_stream4(rp + ch * 32 + i);
-              const float rs = p.res_scale;
-              r.x = (r.x + q.x) * rs; r.y = (r.y + q.y) * rs; r.z = (r.z + q.z) * rs; r.w = (r.w + q.w) * rs;
-            }
-            *reinterpret_cast<float4*>(dp + ch * 32 + i) = r;
-          }
-        }
-      }
+      fwd_epilogue_subtile<BN>(p, tmem_base, quarter, lane, j, qx0[j], qy0[j], n0[j], sub_ok[j], k0);
     }
   }
   ptx::tc_fence_before();
@@ -227,6 +236,136 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant of the forward-form kernel for 256-channel output tiles (option "pair").
+// With fp32 operands the kernel above is bound by the L2 -> SM feed, not by the tensor pipe: per 32-channel step of
+// one tap a CTA fetches 2 x 16 KB of pixels and 32 KB of weights for 8 MMAs (1024 tensor clocks), 64 B/clk per SM
+// or 9.5 KB/clk over 148 SMs against the ~6.3 KB/clk the L2 slices deliver -- a ceiling of about two thirds of the
+// tf32 rate (cuBLAS' tf32 GEMM sits at the same fraction).  Two CTAs on the SMs of one TPC share the weight tile:
+// tcgen05.mma.cta_group::2 multiplies M = 256 pixels (128 per CTA, each CTA's own accumulator lanes) by N = 256
+// output channels of which each CTA stages only 128 rows, so the weight bytes per CTA halve (48 B/clk per SM).
+// Roles per CTA as above; the leader (cluster rank 0) issues the MMAs for both, every TMA load of either CTA counts
+// its bytes on the LEADER's full barrier, and tcgen05.commit multicasts the stage-free / accumulator-ready arrivals
+// to both CTAs.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kPairBBytes = 128 * 128;                       // this CTA's half of the 256-channel weight tile
+constexpr uint32_t kPairStageBytes = kSub * kABytes + kPairBBytes;
+constexpr int kPairStages = 4;
+constexpr uint32_t kPairSmemBytes = kPairStages * kPairStageBytes + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_umma_fwd_pair_kernel(const __grid_constant__ FwdParams p) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kPairStages];
+  __shared__ __align__(8) uint64_t empty_bar[kPairStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int k0 = blockIdx.y * BN;
+  const int nkb = p.ntaps * p.csteps;
+
+  int qx0[kSub], qy0[kSub], n0[kSub];
+  bool sub_ok[kSub];
+  const bool pair = (int)blockIdx.x < p.full_pairs;      // full_pairs is even: both CTAs of a cluster agree
+  const int nsub = pair ? kSub : 1;
+  const int first = pair ? (int)blockIdx.x * kSub : p.full_pairs * kSub + ((int)blockIdx.x - p.full_pairs);
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) {
+    const int id = first + j;
+    sub_ok[j] = j < nsub && id < p.subtiles;
+    const int bx = id % p.tiles_x;
+    const int t = id / p.tiles_x;
+    qx0[j] = bx * p.bw;
+    qy0[j] = (t % p.tiles_y) * p.bh;
+    n0[j] = (t / p.tiles_y) * p.bn;
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kPairStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_pair(ptx::smem_u32(&tmem_slot), 512);
+  ptx::tc_fence_before();
+  __syncwarp();
+  ptx::cluster_sync();               // barriers of both CTAs initialised before any remote arrival
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own pixels, own half of the weight rows; bytes land on the leader's barrier =====
+      ptx::tma_prefetch_desc(&p.w);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = 2u * ((uint32_t)nsub * kABytes + kPairBBytes);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int t = kb / p.csteps;
+        const int c0 = (kb - t * p.csteps) * kBlockK;
+        const TapU tp = p.taps[t];
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full_bar[stage]), stage_tx);
+        const uint32_t fb = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
+        const uint32_t sa = tiles + stage * kPairStageBytes;
+#pragma unroll
+        for (int j = 0; j < kSub; ++j)
+          if (j < nsub) ptx::tma_load_4d_pair(sa + j * kABytes, &p.src[tp.map], fb, c0, qx0[j] + tp.ox, qy0[j] + tp.oy, n0[j]);
+        ptx::tma_load_3d_pair(sa + kSub * kABytes, &p.w, fb, c0, k0 + (int)rank * 128, tp.widx);
+        if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader only) =====
+      constexpr uint32_t idesc = ptx::idesc_tf32(256, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = tiles + stage * kPairStageBytes;
+        const uint64_t bdesc = ptx::smem_desc_sw128(sa + kSub * kABytes, 16, 1024);
+#pragma unroll
+        for (int j = 0; j < kSub; ++j) {
+          if (j >= nsub) break;
+          const uint64_t adesc = ptx::smem_desc_sw128(sa + j * kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            ptx::mma_tf32_pair(tmem_base + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+        }
+        ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 3);   // frees the stage in both CTAs
+        if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::mma_commit_pair(ptx::smem_u32(&accum_bar), 3);
+    }
+  } else {
+    // ===== epilogue: warps 2..5 of each CTA drain that CTA's 128 accumulator lanes =====
+    const int quarter = warp & 3;
+    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < kSub; ++j) {
+      if (j >= nsub) break;
+      fwd_epilogue_subtile<BN>(p, tmem_base, quarter, lane, j, qx0[j], qy0[j], n0[j], sub_ok[j], k0);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncwarp();
+  ptx::cluster_sync();               // the peer's MMAs read this CTA's shared memory: leave together
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -318,6 +457,41 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   dim3 grid(ntiles_n, full_pairs + (p.subtiles - full_pairs * kSub));
   conv_umma_fwd_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(q);
   IDEAS_CHECK_LAUNCH("conv_umma_fwd");
+  return IDEAS_OK;
+}
+
+
+std::atomic<int> g_pair{0};            // option "pair": 256-channel output tiles on CTA pairs (cta_group::2); same speed, see DESIGN.md
+
+int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_umma_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_pair: cudaFuncSetAttribute");
+  // same tail balancing as launch_fwd in units of clusters (2 CTAs, 74 TPCs); both CTAs of a cluster must own the
+  // same number of sub-tiles, so the count of two-sub-tile CTAs is even and the grid is padded to an even height
+  // (a padding CTA computes on TMA zero fill and stores nothing)
+  const int pf = p.subtiles / kSub;
+  int full_pairs = pf & ~1;
+  {
+    const int singles = p.subtiles - full_pairs * kSub;
+    const int total = (full_pairs + ((singles + 1) & ~1)) * ntiles_n;
+    const int tail = total % kNumSMs;
+    if (total > kNumSMs && tail > 0 && tail <= kNumSMs / 2 && g_tail_split.load()) {
+      int cp = ceil_div(tail, ntiles_n);
+      cp = (cp + 1) & ~1;
+      cp = cp > full_pairs ? full_pairs : cp;
+      full_pairs -= cp;
+    }
+  }
+  FwdParams q = p;
+  q.full_pairs = full_pairs;
+  const int singles = p.subtiles - full_pairs * kSub;
+  dim3 grid(full_pairs + ((singles + 1) & ~1), ntiles_n);      // x = pixel tiles: the two CTAs of a cluster are x-neighbours
+  conv_umma_fwd_pair_kernel<<<grid, kThreads, kPairSmemBytes, st>>>(q);
+  IDEAS_CHECK_LAUNCH("conv_umma_fwd_pair");
   return IDEAS_OK;
 }
 
@@ -1297,13 +1471,15 @@ int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
     if (!need[m]) p.src[m] = p.src[need[0] ? 0 : (need[1] ? 1 : (need[2] ? 2 : 3))];
 
   const int BN = (g.OC % 256 == 0) ? 256 : (g.OC % 128 == 0) ? 128 : (g.OC % 64 == 0) ? 64 : 32;
+  const bool use_pair = BN == 256 && g_pair.load() != 0 && p.subtiles >= 4;
   {
     const uint64_t dims[3] = {(uint64_t)g.IC, (uint64_t)g.OC, (uint64_t)(max_widx + 1)};
     const uint64_t strides[2] = {(uint64_t)g.IC * 4, (uint64_t)g.OC * g.IC * 4};
-    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)BN, 1u};
+    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)(use_pair ? 128 : BN), 1u};
     int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
     if (rc) return rc;
   }
+  if (use_pair) return launch_fwd_pair(p, g.OC / 256, st);
   switch (BN) {
     case 256: return launch_fwd<256>(p, g.OC / 256, st);
     case 128: return launch_fwd<128>(p, g.OC / 128, st);
@@ -1684,6 +1860,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dgrad_phases")) {
     if (value < 0 || value > 2) { ideas::set_error("ideas_set_option: dgrad_phases must be 0, 1 or 2"); return IDEAS_ERR_INVALID; }
     ideas::g_dgrad_phases.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pair")) {
+    ideas::g_pair.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "halo_epi")) {

@@ -270,6 +270,42 @@ def test_phased_dgrad_single_launch_matches_per_phase(case):
     assert rel(got, per_phase) <= 2e-5, rel(got, per_phase)
 
 
+PAIR_FWD_CASES = [
+    # N, C, K, H, W, k, stride, pad
+    (2, 64, 256, 16, 16, 3, 1, 1),         # 4 sub-tiles: one cluster of two-sub-tile CTAs
+    (3, 128, 256, 32, 32, 3, 1, 1),
+    (1, 512, 512, 64, 64, 3, 1, 1),        # two 256-channel tiles
+    (5, 96, 256, 20, 12, 3, 1, 1),         # ragged, odd number of sub-tiles (padding CTA)
+    (2, 128, 512, 33, 33, 3, 2, 0),        # stride-2 source (per-parity maps)
+    (7, 256, 256, 9, 9, 1, 1, 0),          # 1x1, 5 sub-tiles
+    (16, 256, 256, 32, 32, 3, 1, 1),       # more CTAs than SMs: tail balancing with single-sub-tile clusters
+    (4, 768, 256, 17, 17, 2, 1, 0),        # 2x2 valid conv
+]
+
+
+@pytest.mark.parametrize("case", PAIR_FWD_CASES)
+def test_pair_forward_matches_simt(case):
+    """conv_umma_fwd_pair_kernel (tcgen05 cta_group::2, option pair) against the FFMA kernel and the one-CTA kernel,
+    with the fused epilogue (demodulation scale, bias, leaky ReLU)."""
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    g = torch.Generator(device="cuda").manual_seed(26)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g)
+    wp = torch.randn(k * k, K, C, device="cuda", generator=g) / (C * k * k) ** 0.5
+    d = torch.rand(N, K, device="cuda", generator=g) + 0.5
+    b = torch.randn(K, device="cuda", generator=g)
+    ref = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_SIMT, d, b, 1)
+    with _opt(b"pmh", 0, 1), _halo(0):
+        with _opt(b"pair", 0, 0):
+            one = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
+        with _opt(b"pair", 1, 0):
+            got = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
+    assert rel(got, one) <= 2e-5, rel(got, one)
+
+
 def test_tf32_error_level_vs_fp64():
     """The tensor path multiplies in TF32 (10-bit mantissa) and accumulates in fp32: report and bound
     its error against an fp64 convolution at the cfg-3 reduction length (K = 9 * 512)."""

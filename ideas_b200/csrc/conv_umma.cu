@@ -241,59 +241,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
 
 
 // ------------------------------------------------------------------------------------------
-// CTA-pair variant of the forward-form kernel for 256-channel output tiles (option "pair").
-// With fp32 operands the kernel above is bound by the L2 -> SM feed, not by the tensor pipe: per 32-channel step of
-// one tap a CTA fetches 2 x 16 KB of pixels and 32 KB of weights for 8 MMAs (1024 tensor clocks), 64 B/clk per SM
-// or 9.5 KB/clk over 148 SMs against the ~6.3 KB/clk the L2 slices deliver -- a ceiling of about two thirds of the
-// tf32 rate (cuBLAS' tf32 GEMM sits at the same fraction).  Two CTAs on the SMs of one TPC share the weight tile:
-// tcgen05.mma.cta_group::2 multiplies M = 256 pixels (128 per CTA, each CTA's own accumulator lanes) by N = 256
-// output channels of which each CTA stages only 128 rows, so the weight bytes per CTA halve (48 B/clk per SM).
-// Roles per CTA as above; the leader (cluster rank 0) issues the MMAs for both, every TMA load of either CTA counts
-// its bytes on the LEADER's full barrier, and tcgen05.commit multicasts the stage-free / accumulator-ready arrivals
-// to both CTAs.
+// CTA-pair, persistent variant of the forward-form kernel for 256-channel output tiles (option "pair").
+// The kernel above leaves the tensor pipe idle for about a quarter of each CTA's life (ncu: pipe active 70 % forward,
+// 80 % data gradient at cfg 3): its two 256-column accumulators fill TMEM, so the epilogue -- 256 KB through four
+// warps -- cannot overlap the next tile, and with one CTA per SM nothing else runs meanwhile.  Here two CTAs on the
+// SMs of one TPC execute ONE tcgen05.mma.cta_group::2 of M = 256 pixels (128 per CTA, each CTA's own accumulator
+// lanes) x N = 256 output channels, each CTA staging its 128 pixels and HALF of the weight tile: the same bytes per
+// flop as above with half the accumulator columns per CTA, which leaves room for TWO accumulator buffers.  The
+// cluster is persistent over a static list of (channel tile, pixel-pair tile) items, so the epilogue of item i runs
+// under the MMAs of item i+1, the TMA producers run ahead across items, and the work granule is 128 pixels per SM
+// instead of 256 (a finer tail).
+//   warp 0  TMA producer (both CTAs): own pixels + own half of the weight rows; all bytes are counted on the LEADER's
+//           full barrier (cp.async.bulk.tensor ... cta_group::2, barrier address via mapa)
+//   warp 1  MMA issuer (leader only) + TMEM owner (tcgen05.alloc.cta_group::2 in both); tcgen05.commit multicasts the
+//           stage-free and accumulator-ready arrivals to both CTAs
+//   warps 2-5 epilogue of this CTA's 128 lanes; "buffer drained" arrives on the leader's barrier from both CTAs
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kPairBBytes = 128 * 128;                       // this CTA's half of the 256-channel weight tile
-constexpr uint32_t kPairStageBytes = kSub * kABytes + kPairBBytes;
-constexpr int kPairStages = 4;
+constexpr uint32_t kPairStageBytes = kABytes + kPairBBytes;       // 32 KB
+constexpr int kPairStages = 6;
 constexpr uint32_t kPairSmemBytes = kPairStages * kPairStageBytes + 1024;
 
+struct alignas(64) PairParams {
+  FwdParams f;
+  int items, ktiles;
+};
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv_umma_fwd_pair_kernel(const __grid_constant__ FwdParams p) {
+conv_umma_fwd_pair_kernel(const __grid_constant__ PairParams pp) {
   constexpr int BN = 256;
+  const FwdParams& p = pp.f;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kPairStages];
   __shared__ __align__(8) uint64_t empty_bar[kPairStages];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t tfull[2];
+  __shared__ __align__(8) uint64_t tempty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int k0 = blockIdx.y * BN;
+  const int cluster_id = (int)blockIdx.x >> 1, nclusters = (int)gridDim.x >> 1;
   const int nkb = p.ntaps * p.csteps;
-
-  int qx0[kSub], qy0[kSub], n0[kSub];
-  bool sub_ok[kSub];
-  const bool pair = (int)blockIdx.x < p.full_pairs;      // full_pairs is even: both CTAs of a cluster agree
-  const int nsub = pair ? kSub : 1;
-  const int first = pair ? (int)blockIdx.x * kSub : p.full_pairs * kSub + ((int)blockIdx.x - p.full_pairs);
-#pragma unroll
-  for (int j = 0; j < kSub; ++j) {
-    const int id = first + j;
-    sub_ok[j] = j < nsub && id < p.subtiles;
-    const int bx = id % p.tiles_x;
-    const int t = id / p.tiles_x;
-    qx0[j] = bx * p.bw;
-    qy0[j] = (t % p.tiles_y) * p.bh;
-    n0[j] = (t / p.tiles_y) * p.bn;
-  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kPairStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
     }
-    ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty[s]), 8);      // four epilogue warps in each of the two CTAs
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc_pair(ptx::smem_u32(&tmem_slot), 512);
@@ -303,26 +302,37 @@ conv_umma_fwd_pair_kernel(const __grid_constant__ FwdParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // item -> (channel tile, this CTA's 128-pixel sub-tile)
+#define IDEAS_PAIR_DECODE(item)                         \
+  const int k0 = ((item) % pp.ktiles) * BN;             \
+  const int sid = ((item) / pp.ktiles) * 2 + (int)rank; \
+  const int bx = sid % p.tiles_x;                       \
+  const int tt = sid / p.tiles_x;                       \
+  const int qx0 = bx * p.bw;                            \
+  const int qy0 = (tt % p.tiles_y) * p.bh;              \
+  const int n0 = (tt / p.tiles_y) * p.bn;
+
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer (both CTAs): own pixels, own half of the weight rows; bytes land on the leader's barrier =====
+      // ===== TMA producer =====
       ptx::tma_prefetch_desc(&p.w);
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_tx = 2u * ((uint32_t)nsub * kABytes + kPairBBytes);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int t = kb / p.csteps;
-        const int c0 = (kb - t * p.csteps) * kBlockK;
-        const TapU tp = p.taps[t];
-        ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
-        if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full_bar[stage]), stage_tx);
-        const uint32_t fb = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
-        const uint32_t sa = tiles + stage * kPairStageBytes;
-#pragma unroll
-        for (int j = 0; j < kSub; ++j)
-          if (j < nsub) ptx::tma_load_4d_pair(sa + j * kABytes, &p.src[tp.map], fb, c0, qx0[j] + tp.ox, qy0[j] + tp.oy, n0[j]);
-        ptx::tma_load_3d_pair(sa + kSub * kABytes, &p.w, fb, c0, k0 + (int)rank * 128, tp.widx);
-        if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+      for (int item = cluster_id; item < pp.items; item += nclusters) {
+        IDEAS_PAIR_DECODE(item)
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int t = kb / p.csteps;
+          const int c0 = (kb - t * p.csteps) * kBlockK;
+          const TapU tp = p.taps[t];
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1u);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full_bar[stage]), 2u * kPairStageBytes);
+          const uint32_t fb = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
+          const uint32_t sa = tiles + stage * kPairStageBytes;
+          // a sub-tile past the end (odd count) has n0 >= N: the box is all out-of-bounds zero fill
+          ptx::tma_load_4d_pair(sa, &p.src[tp.map], fb, c0, qx0 + tp.ox, qy0 + tp.oy, n0);
+          ptx::tma_load_3d_pair(sa + kABytes, &p.w, fb, c0, k0 + (int)rank * 128, tp.widx);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -331,38 +341,47 @@ conv_umma_fwd_pair_kernel(const __grid_constant__ FwdParams p) {
       constexpr uint32_t idesc = ptx::idesc_tf32(256, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+      int it = 0;
+      for (int item = cluster_id; item < pp.items; item += nclusters, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty[buf]), ((uint32_t)(it >> 1) & 1u) ^ 1u);   // both epilogues drained it
         ptx::tc_fence_after();
-        const uint32_t sa = tiles + stage * kPairStageBytes;
-        const uint64_t bdesc = ptx::smem_desc_sw128(sa + kSub * kABytes, 16, 1024);
-#pragma unroll
-        for (int j = 0; j < kSub; ++j) {
-          if (j >= nsub) break;
-          const uint64_t adesc = ptx::smem_desc_sw128(sa + j * kABytes, 16, 1024);
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = tiles + stage * kPairStageBytes;
+          const uint64_t adesc = ptx::smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = ptx::smem_desc_sw128(sa + kABytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            ptx::mma_tf32_pair(tmem_base + j * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            ptx::mma_tf32_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 3);   // frees the stage in both CTAs
+          if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit_pair(ptx::smem_u32(&empty_bar[stage]), 3);   // frees the stage in both CTAs
-        if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
+        ptx::mma_commit_pair(ptx::smem_u32(&tfull[buf]), 3);           // accumulators ready in both CTAs
       }
-      ptx::mma_commit_pair(ptx::smem_u32(&accum_bar), 3);
     }
   } else {
     // ===== epilogue: warps 2..5 of each CTA drain that CTA's 128 accumulator lanes =====
     const int quarter = warp & 3;
-    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
-    ptx::tc_fence_after();
-#pragma unroll
-    for (int j = 0; j < kSub; ++j) {
-      if (j >= nsub) break;
-      fwd_epilogue_subtile<BN>(p, tmem_base, quarter, lane, j, qx0[j], qy0[j], n0[j], sub_ok[j], k0);
+    int it = 0;
+    for (int item = cluster_id; item < pp.items; item += nclusters, ++it) {
+      IDEAS_PAIR_DECODE(item)
+      const int buf = it & 1;
+      ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      fwd_epilogue_subtile<BN>(p, tmem_base, quarter, lane, buf, qx0, qy0, n0, sid < p.subtiles, k0);
+      // every tcgen05.ld of this warp has completed (wait::ld): hand the buffer back to the leader's MMA thread
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tempty[buf]), 0));
     }
   }
+#undef IDEAS_PAIR_DECODE
   ptx::tc_fence_before();
   __syncwarp();
-  ptx::cluster_sync();               // the peer's MMAs read this CTA's shared memory: leave together
+  ptx::cluster_sync();               // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_pair(tmem_base, 512);
@@ -461,7 +480,7 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
 }
 
 
-std::atomic<int> g_pair{0};            // option "pair": 256-channel output tiles on CTA pairs (cta_group::2); same speed, see DESIGN.md
+std::atomic<int> g_pair{1};            // option "pair": 256-channel output tiles on persistent CTA pairs (cta_group::2)
 
 int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   static std::once_flag once;
@@ -470,31 +489,17 @@ int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
     attr_err = cudaFuncSetAttribute(conv_umma_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_pair: cudaFuncSetAttribute");
-  // same tail balancing as launch_fwd in units of clusters (2 CTAs, 74 TPCs); both CTAs of a cluster must own the
-  // same number of sub-tiles, so the count of two-sub-tile CTAs is even and the grid is padded to an even height
-  // (a padding CTA computes on TMA zero fill and stores nothing)
-  const int pf = p.subtiles / kSub;
-  int full_pairs = pf & ~1;
-  {
-    const int singles = p.subtiles - full_pairs * kSub;
-    const int total = (full_pairs + ((singles + 1) & ~1)) * ntiles_n;
-    const int tail = total % kNumSMs;
-    if (total > kNumSMs && tail > 0 && tail <= kNumSMs / 2 && g_tail_split.load()) {
-      int cp = ceil_div(tail, ntiles_n);
-      cp = (cp + 1) & ~1;
-      cp = cp > full_pairs ? full_pairs : cp;
-      full_pairs -= cp;
-    }
-  }
-  FwdParams q = p;
-  q.full_pairs = full_pairs;
-  const int singles = p.subtiles - full_pairs * kSub;
-  dim3 grid(full_pairs + ((singles + 1) & ~1), ntiles_n);      // x = pixel tiles: the two CTAs of a cluster are x-neighbours
-  conv_umma_fwd_pair_kernel<<<grid, kThreads, kPairSmemBytes, st>>>(q);
+  PairParams q;
+  q.f = p;
+  q.ktiles = ntiles_n;
+  const int64_t items = (int64_t)ceil_div(p.subtiles, 2) * ntiles_n;
+  if (items > (1ll << 30)) return IDEAS_ERR_UNSUPPORTED;
+  q.items = (int)items;
+  const int clusters = q.items < kNumSMs / 2 ? q.items : kNumSMs / 2;
+  conv_umma_fwd_pair_kernel<<<2 * clusters, kThreads, kPairSmemBytes, st>>>(q);
   IDEAS_CHECK_LAUNCH("conv_umma_fwd_pair");
   return IDEAS_OK;
 }
-
 
 // ==========================================================================================
 // Halo-reuse kernel (source stride 1, several taps): the implicit GEMM above fetches every shifted

@@ -138,6 +138,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// arrive on a barrier anywhere in the cluster (`bar` is a shared::cluster address, see mapa_shared)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // TMA loads into THIS CTA's shared memory whose completion bytes are counted on a barrier that may live in the peer
 // CTA (`bar` is a shared::cluster address, see mapa_shared)
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2) {

@@ -15,6 +15,8 @@ from ideas_b200._tensor import ptr, stream_ptr
 dev = torch.device("cuda")
 VARIANTS = [("pm one CTA", dict(pair=0, halo=0, pmh=0)), ("pm CTA pair", dict(pair=1, halo=0, pmh=0)),
             ("halo (channel-major)", dict(pair=0, halo=2, pmh=0)), ("pmh (pixel-major halo)", dict(pair=0, halo=0, pmh=2))]
+if len(sys.argv) > 1 and sys.argv[1] == "pair":
+    VARIANTS = VARIANTS[:2]
 CASES = [("forward", 16, 512, 512, 64), ("forward", 32, 256, 256, 128), ("dgrad", 16, 512, 512, 64)]
 
 
@@ -71,5 +73,5 @@ for kind, N, C, K, H in CASES:
         time.sleep(1.0)
     del x, y
     torch.cuda.empty_cache()
-for k, v in dict(pair=0, halo=1, pmh=1).items():
+for k, v in dict(pair=1, halo=1, pmh=1).items():
     _lib.call("ideas_set_option", k.encode(), v)

@@ -296,9 +296,9 @@ def test_pair_forward_matches_simt(case):
     b = torch.randn(K, device="cuda", generator=g)
     ref = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_SIMT, d, b, 1)
     with _opt(b"pmh", 0, 1), _halo(0):
-        with _opt(b"pair", 0, 0):
+        with _opt(b"pair", 0, 1):
             one = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
-        with _opt(b"pair", 1, 0):
+        with _opt(b"pair", 1, 1):
             got = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
     torch.cuda.synchronize()
     assert not torch.isnan(got).any(), "unwritten outputs"

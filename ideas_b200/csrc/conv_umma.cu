@@ -257,19 +257,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
 //           stage-free and accumulator-ready arrivals to both CTAs
 //   warps 2-5 epilogue of this CTA's 128 lanes; "buffer drained" arrives on the leader's barrier from both CTAs
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kPairBBytes = 128 * 128;                       // this CTA's half of the 256-channel weight tile
-constexpr uint32_t kPairStageBytes = kABytes + kPairBBytes;       // 32 KB
-constexpr int kPairStages = 6;
-constexpr uint32_t kPairSmemBytes = kPairStages * kPairStageBytes + 1024;
+template <int BN> struct PairCfg {
+  static constexpr uint32_t kBBytes = (BN / 2) * 128;             // this CTA's half of the BN-channel weight tile
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;      // 32 KB (BN = 256) / 24 KB (BN = 128)
+  static constexpr int kStages = BN == 256 ? 6 : 8;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator buffers
+};
 
 struct alignas(64) PairParams {
   FwdParams f;
   int items, ktiles;
 };
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_umma_fwd_pair_kernel(const __grid_constant__ PairParams pp) {
-  constexpr int BN = 256;
+  using Cfg = PairCfg<BN>;
+  constexpr int kPairStages = Cfg::kStages;
+  constexpr uint32_t kPairStageBytes = Cfg::kStageBytes;
   const FwdParams& p = pp.f;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kPairStages];
@@ -295,7 +301,7 @@ conv_umma_fwd_pair_kernel(const __grid_constant__ PairParams pp) {
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc_pair(ptx::smem_u32(&tmem_slot), 512);
+  if (warp == 1) ptx::tmem_alloc_pair(ptx::smem_u32(&tmem_slot), Cfg::kTmemCols);
   ptx::tc_fence_before();
   __syncwarp();
   ptx::cluster_sync();               // barriers of both CTAs initialised before any remote arrival
@@ -330,7 +336,7 @@ conv_umma_fwd_pair_kernel(const __grid_constant__ PairParams pp) {
           const uint32_t sa = tiles + stage * kPairStageBytes;
           // a sub-tile past the end (odd count) has n0 >= N: the box is all out-of-bounds zero fill
           ptx::tma_load_4d_pair(sa, &p.src[tp.map], fb, c0, qx0 + tp.ox, qy0 + tp.oy, n0);
-          ptx::tma_load_3d_pair(sa + kABytes, &p.w, fb, c0, k0 + (int)rank * 128, tp.widx);
+          ptx::tma_load_3d_pair(sa + kABytes, &p.w, fb, c0, k0 + (int)rank * (BN / 2), tp.widx);
           if (++stage == kPairStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -384,7 +390,7 @@ conv_umma_fwd_pair_kernel(const __grid_constant__ PairParams pp) {
   ptx::cluster_sync();               // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc_pair(tmem_base, 512);
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -482,11 +488,13 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
 
 std::atomic<int> g_pair{1};            // option "pair": 256-channel output tiles on persistent CTA pairs (cta_group::2)
 
+template <int BN>
 int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
+  using Cfg = PairCfg<BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_umma_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes);
+    attr_err = cudaFuncSetAttribute(conv_umma_fwd_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_pair: cudaFuncSetAttribute");
   PairParams q;
@@ -496,7 +504,7 @@ int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   if (items > (1ll << 30)) return IDEAS_ERR_UNSUPPORTED;
   q.items = (int)items;
   const int clusters = q.items < kNumSMs / 2 ? q.items : kNumSMs / 2;
-  conv_umma_fwd_pair_kernel<<<2 * clusters, kThreads, kPairSmemBytes, st>>>(q);
+  conv_umma_fwd_pair_kernel<BN><<<2 * clusters, kThreads, Cfg::kSmemBytes, st>>>(q);
   IDEAS_CHECK_LAUNCH("conv_umma_fwd_pair");
   return IDEAS_OK;
 }
@@ -1476,15 +1484,28 @@ int umma_conv_launch(const ConvGeom& g, float* dst, const float* src, const floa
     if (!need[m]) p.src[m] = p.src[need[0] ? 0 : (need[1] ? 1 : (need[2] ? 2 : 3))];
 
   const int BN = (g.OC % 256 == 0) ? 256 : (g.OC % 128 == 0) ? 128 : (g.OC % 64 == 0) ? 64 : 32;
-  const bool use_pair = BN == 256 && g_pair.load() != 0 && p.subtiles >= 4;
+  // option "pair": 0 = never, 1 = heuristic, 2 = every 256- and 128-channel tile, 3 = 256-channel tiles only.
+  // 256-channel tiles: always (1.0-1.65x, scripts/bench_pair.py).  128-channel tiles gain where the overlapped
+  // epilogue and the finer granule matter (fused activation or stride-2 source, several rounds of items: 1.16-1.32x)
+  // and lose on short launches (384-channel layers at 16x16: 0.7x) and plain data gradients (0.93x).
+  const int pair_mode = g_pair.load();
+  bool use_pair = false;
+  if (p.subtiles >= 4) {
+    if (BN == 256) use_pair = pair_mode >= 1;
+    if (BN == 128) {
+      const int64_t items = (int64_t)ceil_div(p.subtiles, 2) * (g.OC / 128);
+      use_pair = pair_mode == 2 ||
+                 (pair_mode == 1 && items >= 3 * (kNumSMs / 2) && (g.i_s == 2 || act != IDEAS_ACT_NONE));
+    }
+  }
   {
     const uint64_t dims[3] = {(uint64_t)g.IC, (uint64_t)g.OC, (uint64_t)(max_widx + 1)};
     const uint64_t strides[2] = {(uint64_t)g.IC * 4, (uint64_t)g.OC * g.IC * 4};
-    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)(use_pair ? 128 : BN), 1u};
+    const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)(use_pair ? BN / 2 : BN), 1u};
     int rc = encode_map(&p.w, w, 3, dims, strides, wbox);
     if (rc) return rc;
   }
-  if (use_pair) return launch_fwd_pair(p, g.OC / 256, st);
+  if (use_pair) return BN == 256 ? launch_fwd_pair<256>(p, g.OC / 256, st) : launch_fwd_pair<128>(p, g.OC / 128, st);
   switch (BN) {
     case 256: return launch_fwd<256>(p, g.OC / 256, st);
     case 128: return launch_fwd<128>(p, g.OC / 128, st);

@@ -10,10 +10,18 @@ from ideas_b200 import _lib
 from ideas_b200._tensor import ptr, stream_ptr
 
 dev = torch.device("cuda")
+MODES = (0, 1)
+CASES128 = [("forward", 32, 128, 128, 128, 3, 1, 1), ("forward", 32, 256, 384, 16, 3, 1, 1), ("forward", 32, 384, 384, 16, 3, 1, 1),
+            ("forward", 32, 64, 128, 129, 3, 2, 0), ("forward", 32, 256, 128, 256, 1, 1, 0), ("forward", 96, 128, 128, 64, 3, 1, 1),
+            ("dgrad", 32, 128, 128, 128, 3, 1, 1), ("dgrad", 32, 384, 384, 16, 3, 1, 1), ("dgrad", 96, 128, 128, 64, 3, 1, 1)]
 CASES = [("forward", 16, 512, 512, 64, 3, 1, 1), ("forward", 32, 512, 512, 64, 3, 1, 1), ("forward", 32, 256, 256, 128, 3, 1, 1),
          ("forward", 32, 512, 512, 32, 3, 1, 1), ("forward", 32, 512, 512, 16, 3, 1, 1), ("forward", 32, 256, 512, 65, 3, 2, 0),
          ("forward", 32, 128, 256, 129, 3, 2, 0), ("forward", 96, 256, 256, 32, 3, 1, 1),
          ("dgrad", 32, 512, 512, 64, 3, 1, 1), ("dgrad", 32, 256, 256, 128, 3, 1, 1), ("dgrad", 32, 512, 512, 32, 3, 1, 1)]
+if len(sys.argv) > 1 and sys.argv[1] == "128":       # 128-channel tiles: pair mode 2 vs 0, halo / pmh heuristics off
+    CASES, MODES = CASES128, (0, 2)
+    _lib.call("ideas_set_option", b"halo", 0)
+    _lib.call("ideas_set_option", b"pmh", 0)
 print(f"{'kind':8s} {'N':>5s} {'C':>4s} {'K':>4s} {'H':>4s} k s p | pair=0 ms  TF/s | pair=1 ms  TF/s | speed-up")
 for kind, N, C, K, H, k, s, pad in CASES:
     OH = (H + 2 * pad - k) // s + 1
@@ -32,7 +40,7 @@ for kind, N, C, K, H, k, s, pad in CASES:
                                s, pad, OH, OH, 0, 0.2, 1.0, 0, st)
     flops = 2.0 * N * OH * OH * K * C * k * k
     res = []
-    for mode in (0, 1):
+    for mode in MODES:
         _lib.call("ideas_set_option", b"pair", mode)
         for _ in range(3):
             fn()

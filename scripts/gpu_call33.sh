@@ -1,0 +1,3 @@
+#!/bin/bash
+timeout 300 python -m pytest tests/test_gpu_umma.py -m gpu -q -x -k "pair" 2>&1 | tail -8
+timeout 300 python scripts/bench_pair.py 128 2>&1 | tail -11

@@ -280,6 +280,10 @@ PAIR_FWD_CASES = [
     (7, 256, 256, 9, 9, 1, 1, 0),          # 1x1, 5 sub-tiles
     (16, 256, 256, 32, 32, 3, 1, 1),       # more CTAs than SMs: tail balancing with single-sub-tile clusters
     (4, 768, 256, 17, 17, 2, 1, 0),        # 2x2 valid conv
+    (3, 64, 128, 32, 32, 3, 1, 1),         # 128-channel tiles (pair mode 2): each CTA stages 64 weight rows
+    (2, 256, 384, 16, 16, 3, 1, 1),        # 384 = 3 x 128 (G's third block)
+    (5, 96, 128, 20, 12, 3, 1, 1),
+    (2, 128, 128, 65, 65, 3, 2, 0),
 ]
 
 
@@ -298,7 +302,7 @@ def test_pair_forward_matches_simt(case):
     with _opt(b"pmh", 0, 1), _halo(0):
         with _opt(b"pair", 0, 1):
             one = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
-        with _opt(b"pair", 1, 1):
+        with _opt(b"pair", 2, 1):
             got = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
     torch.cuda.synchronize()
     assert not torch.isnan(got).any(), "unwritten outputs"

@@ -25,8 +25,10 @@ for N, C, K, H in CASES:
                            s, pad, OH, OH, 0, 0.2, 1.0, 0, st)
     flops = 2.0 * N * OH * OH * K * C * k * k
     res = []
-    for mode in (0, 2):
-        _lib.call("ideas_set_option", b"dgrad_phases", mode)
+    for mode in (0, 2, -1):
+        # -1: halo kernel off -> one launch per phase of the pixel-major kernels (CTA pairs for 256-channel tiles)
+        _lib.call("ideas_set_option", b"halo", 0 if mode < 0 else 1)
+        _lib.call("ideas_set_option", b"dgrad_phases", max(mode, 0))
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
@@ -38,7 +40,9 @@ for N, C, K, H in CASES:
         torch.cuda.synchronize()
         res.append(a.elapsed_time(e) / 5)
     print(f"{N:5d} {C:4d} {K:4d} {H:4d} | {res[0]:7.3f} {flops / res[0] / 1e9:6.1f} | "
-          f"{res[1]:7.3f} {flops / res[1] / 1e9:6.1f} | {res[0] / res[1]:5.2f}x", flush=True)
+          f"{res[1]:7.3f} {flops / res[1] / 1e9:6.1f} | {res[0] / res[1]:5.2f}x | pixel-major per phase {res[2]:7.3f} "
+          f"{flops / res[2] / 1e9:6.1f}", flush=True)
     del x, y
     torch.cuda.empty_cache()
 _lib.call("ideas_set_option", b"dgrad_phases", 1)
+_lib.call("ideas_set_option", b"halo", 1)

@@ -260,26 +260,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
 template <int BN> struct PairCfg {
   static constexpr uint32_t kBBytes = (BN / 2) * 128;             // this CTA's half of the BN-channel weight tile
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;      // 32 KB (BN = 256) / 24 KB (BN = 128)
-  static constexpr int kStages = BN == 256 ? 6 : 8;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kMaxStages = (226 * 1024) / kStageBytes;   // 7 / 9: all of the 227 KB a CTA can have
+  static constexpr int kStages = BN == 256 ? 6 : 8;               // default ring depth (option "pair_stages")
   static constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator buffers
 };
 
 struct alignas(64) PairParams {
   FwdParams f;
-  int items, ktiles;
+  int items, ktiles, stages;
 };
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_umma_fwd_pair_kernel(const __grid_constant__ PairParams pp) {
   using Cfg = PairCfg<BN>;
-  constexpr int kPairStages = Cfg::kStages;
+  constexpr int kPairMaxStages = Cfg::kMaxStages;
+  const int kPairStages = pp.stages;
   constexpr uint32_t kPairStageBytes = Cfg::kStageBytes;
   const FwdParams& p = pp.f;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kPairStages];
-  __shared__ __align__(8) uint64_t empty_bar[kPairStages];
+  __shared__ __align__(8) uint64_t full_bar[kPairMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kPairMaxStages];
   __shared__ __align__(8) uint64_t tfull[2];
   __shared__ __align__(8) uint64_t tempty[2];
   __shared__ uint32_t tmem_slot;
@@ -486,6 +487,7 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
 }
 
 
+std::atomic<int> g_pair_stages{0};     // option "pair_stages": TMA ring depth of the pair kernel (0 = default)
 std::atomic<int> g_pair{1};            // option "pair": 256-channel output tiles on persistent CTA pairs (cta_group::2)
 
 template <int BN>
@@ -494,7 +496,8 @@ int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_umma_fwd_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr_err = cudaFuncSetAttribute(conv_umma_fwd_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::kMaxStages * Cfg::kStageBytes + 1024);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_pair: cudaFuncSetAttribute");
   PairParams q;
@@ -503,8 +506,10 @@ int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   const int64_t items = (int64_t)ceil_div(p.subtiles, 2) * ntiles_n;
   if (items > (1ll << 30)) return IDEAS_ERR_UNSUPPORTED;
   q.items = (int)items;
+  const int want = g_pair_stages.load();
+  q.stages = want >= 2 && want <= Cfg::kMaxStages ? want : Cfg::kStages;
   const int clusters = q.items < kNumSMs / 2 ? q.items : kNumSMs / 2;
-  conv_umma_fwd_pair_kernel<BN><<<2 * clusters, kThreads, Cfg::kSmemBytes, st>>>(q);
+  conv_umma_fwd_pair_kernel<BN><<<2 * clusters, kThreads, q.stages * Cfg::kStageBytes + 1024, st>>>(q);
   IDEAS_CHECK_LAUNCH("conv_umma_fwd_pair");
   return IDEAS_OK;
 }
@@ -1886,6 +1891,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dgrad_phases")) {
     if (value < 0 || value > 2) { ideas::set_error("ideas_set_option: dgrad_phases must be 0, 1 or 2"); return IDEAS_ERR_INVALID; }
     ideas::g_dgrad_phases.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pair_stages")) {
+    ideas::g_pair_stages.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "pair")) {

@@ -438,7 +438,13 @@ def run_ours(args):
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    out = sys.stdout
     if world > 1:
+        # stdout carries exactly one JSON line.  NCCL writes its version banner (and NCCL_DEBUG output) to file
+        # descriptor 1 from C, so the descriptor itself is pointed at stderr and the JSON line goes to a saved copy.
+        sys.stdout.flush()
+        out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     roof = None
@@ -565,7 +571,7 @@ def run_ours(args):
                 line["cpu_baseline"] = {"value": CPU_BATCH / t, "unit": UNIT, "cores": cores, "kind": kind,
                                         "sample": f"{n} train iteration(s) on {CPU_BATCH} images {S}x{S} "
                                                   f"({'unmodified reference' if kind == 'reference' else 'oracle port of train.py:33-221'}), {t:.1f} s each"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         # Orderly teardown: the captured graphs hold NCCL work, so they go first, then the communicator.  A watchdog
         # still ends the process if the teardown blocks (round 1 observed destroy_process_group hanging with live

@@ -260,15 +260,86 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_fwd_kernel(const __grid
 template <int BN> struct PairCfg {
   static constexpr uint32_t kBBytes = (BN / 2) * 128;             // this CTA's half of the BN-channel weight tile
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;      // 32 KB (BN = 256) / 24 KB (BN = 128)
-  static constexpr int kMaxStages = (226 * 1024) / kStageBytes;   // 7 / 9: all of the 227 KB a CTA can have
+  static constexpr uint32_t kEpiBytes = 4 * 2 * 4096;             // two 4 KB TMA-store staging tiles per epilogue warp
+  static constexpr int kMaxStages = (226 * 1024 - kEpiBytes) / kStageBytes;   // 6 / 8: all of the 227 KB a CTA can have
   static constexpr int kStages = BN == 256 ? 6 : 8;               // default ring depth (option "pair_stages")
   static constexpr uint32_t kTmemCols = 2 * BN;                   // two accumulator buffers
 };
 
 struct alignas(64) PairParams {
   FwdParams f;
+  CUtensorMap dst;      // output as {OC, QW, QH, N} with the phase offset / stride folded in (TMA-store epilogue)
   int items, ktiles, stages;
+  int epi;              // 1 = epilogue through shared memory + TMA store, 0 = direct 128-bit stores
+  int wy, wn;           // a warp's 32 accumulator rows as a box: bw x wy x wn pixels
 };
+
+// Epilogue of one 128-pixel sub-tile through shared memory and TMA stores (pair kernel).  A warp owns 32 accumulator
+// rows = a (bw x wy x wn)-pixel box.  Per 32-channel chunk: tcgen05.ld -> demodulation, bias, leaky ReLU, residual in
+// registers -> the thread's 128-byte row into a 4 KB staging tile in the 128-byte-swizzle pattern (conflict-free
+// 16-byte stores) -> fence.proxy.async -> one cp.async.bulk.tensor store of the box.  Pixels outside the image are
+// clipped by the TMA unit, so there are no store predicates and no per-pixel address arithmetic; two staging tiles per
+// warp let the store of chunk i drain under the arithmetic of chunk i+1.
+template <int BN>
+__device__ __forceinline__ void pair_epilogue_tma(const PairParams& pp, uint32_t tmem_base, uint32_t stage_smem, int quarter,
+                                                  int lane, int buf, int qx0, int qy0, int n0, bool sub_ok, int k0,
+                                                  uint32_t& nstores) {
+  const FwdParams& p = pp.f;
+  const int row = quarter * 32 + lane;
+  const int wq = row % p.bw;
+  const int t = row / p.bw;
+  const int qx = qx0 + wq, qy = qy0 + (t % p.bh), n = n0 + t / p.bh;
+  const bool valid = sub_ok && n < p.N && qy < p.QH && qx < p.QW;      // guards the per-pixel LOADS only
+  const float* os = nullptr;
+  const float* rp = nullptr;
+  if (valid) {
+    if (p.residual)
+      rp = p.residual + (((int64_t)n * p.OH + (qy * p.o_s + p.o_py)) * p.OW + (qx * p.o_s + p.o_px)) * p.OC + k0;
+    if (p.out_scale) os = p.out_scale + (int64_t)n * p.OC + k0;
+  }
+  // box origin of this warp's 32 rows
+  const int t0 = (quarter * 32) / p.bw;
+  const int by = qy0 + (t0 % p.bh), bn = n0 + t0 / p.bh;
+  const uint32_t rowoff = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    float v[32];
+    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + ch * 32), v);
+    const uint32_t tile = stage_smem + (nstores & 1u) * 4096u;
+    if (lane == 0) ptx::tma_store_wait_read<1>();        // the store that last read this tile has drained it
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      if (os) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(os + ch * 32 + i));
+        r.x *= s.x; r.y *= s.y; r.z *= s.z; r.w *= s.w;
+      }
+      if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + k0 + ch * 32 + i));
+        r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+      }
+      if (p.act == IDEAS_ACT_LRELU) {
+        r.x = lrelu(r.x, p.alpha) * p.gain; r.y = lrelu(r.y, p.alpha) * p.gain;
+        r.z = lrelu(r.z, p.alpha) * p.gain; r.w = lrelu(r.w, p.alpha) * p.gain;
+      }
+      if (rp) {
+        const float4 q = ld_stream4(rp + ch * 32 + i);
+        const float rs = p.res_scale;
+        r.x = (r.x + q.x) * rs; r.y = (r.y + q.y) * rs; r.z = (r.z + q.z) * rs; r.w = (r.w + q.w) * rs;
+      }
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                   ::"r"(tile + rowoff + ((((uint32_t)i >> 2) ^ sw) << 4)), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w)
+                   : "memory");
+    }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_4d(&pp.dst, tile, k0 + ch * 32, qx0, by, bn);
+      ptx::tma_store_commit();
+    }
+    ++nstores;
+  }
+}
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -372,18 +443,24 @@ conv_umma_fwd_pair_kernel(const __grid_constant__ PairParams pp) {
   } else {
     // ===== epilogue: warps 2..5 of each CTA drain that CTA's 128 accumulator lanes =====
     const int quarter = warp & 3;
+    const uint32_t epi_smem = tiles + (uint32_t)kPairStages * kPairStageBytes + (uint32_t)(warp - 2) * 8192u;
+    uint32_t nstores = 0;
     int it = 0;
     for (int item = cluster_id; item < pp.items; item += nclusters, ++it) {
       IDEAS_PAIR_DECODE(item)
       const int buf = it & 1;
       ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
-      fwd_epilogue_subtile<BN>(p, tmem_base, quarter, lane, buf, qx0, qy0, n0, sid < p.subtiles, k0);
+      if (pp.epi)
+        pair_epilogue_tma<BN>(pp, tmem_base, epi_smem, quarter, lane, buf, qx0, qy0, n0, sid < p.subtiles, k0, nstores);
+      else
+        fwd_epilogue_subtile<BN>(p, tmem_base, quarter, lane, buf, qx0, qy0, n0, sid < p.subtiles, k0);
       // every tcgen05.ld of this warp has completed (wait::ld): hand the buffer back to the leader's MMA thread
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tempty[buf]), 0));
     }
+    if (lane == 0) ptx::tma_store_wait<0>();             // every bulk store of this warp has completed
   }
 #undef IDEAS_PAIR_DECODE
   ptx::tc_fence_before();
@@ -414,7 +491,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // fp32 tensor viewed as rank-`rank` (innermost first), 128-byte swizzle, zero OOB fill
 int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+               const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, bool plain_f32 = false) {
   auto enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -424,7 +501,9 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  const CUtensorMapDataType dt = g_tma_tf32.load() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  // loads round fp32 to tf32 in the TMA unit (option tma_tf32); stores must keep the fp32 bits
+  const CUtensorMapDataType dt =
+      (g_tma_tf32.load() && !plain_f32) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -487,6 +566,7 @@ int launch_fwd(const FwdParams& p, int ntiles_n, cudaStream_t st) {
 }
 
 
+std::atomic<int> g_pair_epi{1};        // option "pair_epi": pair kernel epilogue through shared memory + TMA store (1) or direct stores (0)
 std::atomic<int> g_pair_stages{0};     // option "pair_stages": TMA ring depth of the pair kernel (0 = default)
 std::atomic<int> g_pair{1};            // option "pair": 256-channel output tiles on persistent CTA pairs (cta_group::2)
 
@@ -497,7 +577,7 @@ int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(conv_umma_fwd_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::kMaxStages * Cfg::kStageBytes + 1024);
+                                    Cfg::kMaxStages * Cfg::kStageBytes + Cfg::kEpiBytes + 1024);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "conv_umma_pair: cudaFuncSetAttribute");
   PairParams q;
@@ -508,8 +588,23 @@ int launch_fwd_pair(const FwdParams& p, int ntiles_n, cudaStream_t st) {
   q.items = (int)items;
   const int want = g_pair_stages.load();
   q.stages = want >= 2 && want <= Cfg::kMaxStages ? want : Cfg::kStages;
+  // TMA-store epilogue: the output seen as {OC, QW, QH, N} -- phase offset in the base, destination stride in the
+  // strides -- so a warp's 32 accumulator rows (bw x wy x wn pixels) are one box and the edges are clipped by the unit
+  q.epi = g_pair_epi.load() ? 1 : 0;
+  q.wy = p.bh < 32 / p.bw ? p.bh : 32 / p.bw;
+  q.wn = 32 / (p.bw * q.wy);
+  if (q.epi) {
+    const uint64_t dims[4] = {(uint64_t)p.OC, (uint64_t)p.QW, (uint64_t)p.QH, (uint64_t)p.N};
+    const uint64_t strides[3] = {(uint64_t)p.o_s * p.OC * 4, (uint64_t)p.o_s * p.OW * p.OC * 4, (uint64_t)p.OH * p.OW * p.OC * 4};
+    const uint32_t box[4] = {32u, (uint32_t)p.bw, (uint32_t)q.wy, (uint32_t)q.wn};
+    float* base = p.dst + ((int64_t)p.o_py * p.OW + p.o_px) * p.OC;
+    int rc = encode_map(&q.dst, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (rc) return rc;
+  } else {
+    memset(&q.dst, 0, sizeof(q.dst));
+  }
   const int clusters = q.items < kNumSMs / 2 ? q.items : kNumSMs / 2;
-  conv_umma_fwd_pair_kernel<BN><<<2 * clusters, kThreads, q.stages * Cfg::kStageBytes + 1024, st>>>(q);
+  conv_umma_fwd_pair_kernel<BN><<<2 * clusters, kThreads, q.stages * Cfg::kStageBytes + Cfg::kEpiBytes + 1024, st>>>(q);
   IDEAS_CHECK_LAUNCH("conv_umma_fwd_pair");
   return IDEAS_OK;
 }
@@ -1891,6 +1986,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dgrad_phases")) {
     if (value < 0 || value > 2) { ideas::set_error("ideas_set_option: dgrad_phases must be 0, 1 or 2"); return IDEAS_ERR_INVALID; }
     ideas::g_dgrad_phases.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "pair_epi")) {
+    ideas::g_pair_epi.store(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "pair_stages")) {

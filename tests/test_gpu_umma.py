@@ -304,10 +304,35 @@ def test_pair_forward_matches_simt(case):
             one = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
         with _opt(b"pair", 2, 1):
             got = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
+            with _opt(b"pair_epi", 0, 1):
+                direct = conv_forward(x, wp, N, H, W, C, K, k, k, stride, pad, L.IMPL_UMMA, d, b, 1)
     torch.cuda.synchronize()
     assert not torch.isnan(got).any(), "unwritten outputs"
     assert rel(got, ref) <= 1e-3, rel(got, ref)
     assert rel(got, one) <= 2e-5, rel(got, one)
+    assert torch.equal(got, direct)          # TMA-store epilogue vs direct stores: the same bits
+
+
+@pytest.mark.parametrize("epi", [0, 1])
+@pytest.mark.parametrize("case", [(1, 256, 256, 65, 65, 3, 2, 0), (2, 512, 256, 17, 17, 3, 2, 0), (2, 256, 128, 33, 33, 3, 1, 1),
+                                  (3, 256, 64, 31, 31, 1, 2, 0), (2, 128, 256, 33, 29, 3, 2, 0)])
+def test_pair_dgrad_matches_simt(case, epi):
+    """Data gradients on the CTA-pair kernel (halo / pmh kernels off): strided destinations -- the TMA-store epilogue
+    (pair_epi=1) writes each output phase through a tensor map whose strides skip the other phases -- and both
+    epilogue variants."""
+    L = _lib()
+    N, C, K, H, W, k, stride, pad = case
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(27)
+    dy = torch.randn(N, OH, OW, K, device="cuda", generator=g)
+    wpt = torch.randn(k * k, C, K, device="cuda", generator=g) / (K * k * k) ** 0.5
+    s = torch.rand(N, C, device="cuda", generator=g) + 0.5
+    ref = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_SIMT, s)
+    with _opt(b"pmh", 0, 1), _halo(0), _opt(b"dgrad_phases", 0, 1), _opt(b"pair", 2, 1), _opt(b"pair_epi", epi, 1):
+        got = conv_dgrad(dy, wpt, N, H, W, C, K, k, k, stride, pad, OH, OW, L.IMPL_AUTO, s)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), "unwritten outputs"
+    assert rel(got, ref) <= 1e-3, rel(got, ref)
 
 
 def test_tf32_error_level_vs_fp64():

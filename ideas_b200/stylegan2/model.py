@@ -237,7 +237,8 @@ class ModulatedConv2d(nn.Module):
         wp, wsq = self.derived_weights()
         d = None
         if self.demodulate:
-            d = torch.rsqrt((s * s) @ wsq.t() + self.eps)            # (B, Cout)
+            # (B, Cout); the (s^2) . sum_k w^2 product on the repo's own fp32 GEMM like every other linear map here
+            d = torch.rsqrt(matmul_nt(s * s, wsq) + self.eps)
         act = activation is not None
         bias = activation.bias if act else None
         alpha = activation.negative_slope if act else 0.2

@@ -31,7 +31,7 @@ from torch.autograd.function import once_differentiable
 from ... import _lib
 from ..._tensor import empty_nhwc, nhwc, ptr, require_cuda, stream_ptr
 from .fused_act import FusedLeakyReLUFunctionBackward
-from .upfirdn2d import UpFirDn2dBackward, _grad_pad, _run as _upfirdn_run
+from .upfirdn2d import UpFirDn2dBackward, _grad_pad, flipped, _run as _upfirdn_run
 
 import os
 
@@ -244,7 +244,8 @@ class ConvFwd(Function):
         want_bias = ctx.has_bias and ctx.needs_input_grad[2]
         gb = gres = None
         if ctx.res_scale is not None:
-            gy = gy * ctx.res_scale                    # one pass serves the residual branch and this convolution
+            if ctx.res_scale != 1.0:                   # (the residual blocks fold their 1/sqrt(2) into weights: no pass)
+                gy = gy * ctx.res_scale                # one pass serves the residual branch and this convolution
             gres = gy if ctx.needs_input_grad[7] else None
         if ctx.act != _lib.ACT_NONE:
             gy, gb = FusedLeakyReLUFunctionBackward.apply(gy, out, want_bias, ctx.alpha, ctx.gain)
@@ -337,7 +338,7 @@ class ConvActBlur(Function):
         y = _fwd(x, wp, g, bias=bias, act=_lib.ACT_LRELU, alpha=alpha, gain=gain)
         pad4 = (pad[0], pad[1], pad[0], pad[1])
         z = _upfirdn_run(y, kernel, (1, 1), (1, 1), pad4)
-        ctx.save_for_backward(x, wp, y, kernel, torch.flip(kernel, [0, 1]))
+        ctx.save_for_backward(x, wp, y, kernel, flipped(kernel))
         ctx.cfg = (g, alpha, gain, pad4, (z.shape[2], z.shape[3]))
         return z
 
@@ -665,7 +666,7 @@ class ModConvUp(Function):
                 g1 = gy
         g_pad = _grad_pad((u.shape[2], u.shape[3]), (g1.shape[2], g1.shape[3]), kernel.shape, (1, 1), (1, 1),
                           ctx.blur_pad)
-        gkernel = torch.flip(kernel, [0, 1])
+        gkernel = flipped(kernel)
         gd = None
         if d is not None and _blur_act_bwd_ok(g.C, kernel, g.N):
             # blur^T, the demodulation scale and dL/dd = sum_p gu * u / d in ONE kernel: the blurred gradient is

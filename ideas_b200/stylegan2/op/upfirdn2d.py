@@ -27,6 +27,13 @@ def residual_ok(x, kernel, up, down) -> bool:
         x.shape[1] % 4 == 0 and x.shape[0] <= 65535
 
 
+def flipped(kernel):
+    """torch.flip(kernel, [0, 1]) -- the taps of the adjoint -- once per training iteration and stream instead of one
+    tiny launch per call (the per-step cache lives in op/conv.py, which imports this module)."""
+    from .conv import cached
+    return cached(kernel, "flip", lambda: torch.flip(kernel, [0, 1]), immutable=True)
+
+
 def _run(x, kernel, up, down, pad, bias=None, alpha=0.2, gain=1.0, residual=None, res_scale=1.0):
     """x: NHWC-dense (N,C,H,W) tensor.  pad = (x0, x1, y0, y1)."""
     n, c, h, w = x.shape
@@ -80,7 +87,7 @@ class UpFirDn2d(Function):
         kernel = kernel.contiguous()
         x = nhwc(input)
         out = _run(x, kernel, up, down, pad, residual=nhwc(residual) if residual is not None else None, res_scale=res_scale)
-        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        ctx.save_for_backward(kernel, flipped(kernel))
         ctx.cfg = (up, down, pad, tuple(input.shape), (out.shape[2], out.shape[3]))
         ctx.res_scale = res_scale if residual is not None else None
         return out
@@ -91,7 +98,8 @@ class UpFirDn2d(Function):
         up, down, pad, in_size, out_size = ctx.cfg
         gres = None
         if ctx.res_scale is not None:
-            grad_output = grad_output * ctx.res_scale
+            if ctx.res_scale != 1.0:                   # folded residual blocks pass 1.0: no scaling pass
+                grad_output = grad_output * ctx.res_scale
             gres = grad_output if ctx.needs_input_grad[5] else None
         g_pad = _grad_pad(in_size[2:], out_size, kernel.shape, up, down, pad)
         gx = UpFirDn2dBackward.apply(grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size)
@@ -111,7 +119,7 @@ class SplitDown(Function):
         kernel = kernel.contiguous()
         x = nhwc(x)
         low = _run(x, kernel, (1, 1), (2, 2), pad)
-        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        ctx.save_for_backward(kernel, flipped(kernel))
         ctx.cfg = (pad, tuple(x.shape), (low.shape[2], low.shape[3]))
         ctx.set_materialize_grads(False)
         return x.view_as(x), low
@@ -141,7 +149,7 @@ class BlurBiasAct(Function):
         kernel = kernel.contiguous()
         x = nhwc(input)
         out = _run(x, kernel, (1, 1), (1, 1), pad, bias=bias, alpha=negative_slope, gain=scale)
-        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]), out)
+        ctx.save_for_backward(kernel, flipped(kernel), out)
         ctx.cfg = (pad, tuple(input.shape), (out.shape[2], out.shape[3]), negative_slope, scale)
         return out
 

@@ -639,7 +639,8 @@ constexpr int kHaloSlack = 24;                // rows past the box that rounding
 constexpr uint32_t kHaloSmemBudget = 224 * 1024;
 constexpr uint32_t kHaloStageBytes = kHaloEpiWarps * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
 std::atomic<int> g_dgrad_phases{1};          // option "dgrad_phases": strided data gradients: all phases in one halo launch
-std::atomic<int> g_halo_epi{1};               // option "halo_epi": 1 = transposed 128-bit-store epilogue, 0 = per-element stores
+std::atomic<int> g_halo_epi{1};               // option "halo_epi": 0 = per-element stores, 1 = TMA-store epilogue on 32-wide tiles and the
+                                              // transposed 128-bit-store epilogue elsewhere, 3 = transposed epilogue everywhere
 
 std::atomic<int> g_halo_mode{1};              // 0 = never, 1 = heuristic, 2 = whenever eligible
 
@@ -674,6 +675,7 @@ struct alignas(64) HaloParams {
   int nphase;
   struct Phase { int ntaps, tap0, o_py, o_px, QH, QW, x_org, y_org; } ph[4];
   TapH taps[kMaxTaps];
+  CUtensorMap dmap[4];    // epi == 2: the output of each phase as {OC, QW, QH, N} for the TMA-store epilogue
 };
 
 __device__ __forceinline__ void st_global_pred(float* p, float v, bool pred) {
@@ -843,6 +845,46 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
       ptx::mbar_wait(ptx::smem_u32(&tfull[buf]), (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 256;
+      if (p.epi == 2) {
+        // TMA-store epilogue (tile width a multiple of 32): segment sx of tile row y is the 32 accumulator columns
+        // from y*bwp + sx on, i.e. 32 consecutive pixels of one image row.  The thread (= one output channel) finishes them and writes
+        // them as a column of the warp's 32 pixel x 32 channel staging tile in the 128-byte-swizzle pattern (a warp
+        // store is one permuted 128-byte row: conflict-free); one cp.async.bulk.tensor store then writes the
+        // {32 channels, 32 pixels} box.  The unit clips the box at the image edges and at OC, and the tensor map of
+        // the phase carries the destination stride, so there is no address arithmetic, no predicate and no read-back.
+        const uint32_t stage = xring + p.x_stages * p.x_slot_bytes + (uint32_t)(warp - 3) * 4096u;
+        const uint32_t colw = (uint32_t)(lane & 3) * 4u, chunk = (uint32_t)(lane >> 2);
+        const int nseg = p.bw >> 5;                              // 32-pixel segments per tile row (bw % 32 == 0)
+        const int nunits = xlim > 0 ? ylim * nseg : 0;           // rows / tiles outside this phase's grid: nothing to store
+        for (int u = half; u < nunits; u += 2) {
+          const int y = u / nseg, sx = (u - y * nseg) << 5;
+          float v[32];
+          ptx::tmem_ld_32x32(acc + (uint32_t)(y * p.bwp + sx), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float r = fmaf(v[j], os, bs);
+            r = (lrelu_on && r < 0.f) ? r * alpha : r;
+            v[j] = r * gain;
+          }
+          if (lane == 0) ptx::tma_store_wait_read<0>();        // the previous store has drained the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            asm volatile("st.shared.f32 [%0], %1;"
+                         ::"r"(stage + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4) + colw), "f"(v[j])
+                         : "memory");
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_4d(&p.dmap[phs], stage, k0 + quarter * 32, qx0 + sx, qy0 + y, n);
+            ptx::tma_store_commit();
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ptx::smem_u32(&tempty[buf]));
+        continue;
+      }
       if (p.epi) {
         // Transposed epilogue: tcgen05.ld hands a thread (= one output channel) 32 consecutive pixels.  The thread
         // finishes them (demodulation, bias, leaky ReLU: per-channel scalars), writes them as one COLUMN of a private
@@ -916,6 +958,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_umma_halo_kernel(const _
       __syncwarp();
       if (lane == 0) mbar_arrive(ptx::smem_u32(&tempty[buf]));
     }
+    if (p.epi == 2 && lane == 0) ptx::tma_store_wait<0>();     // every bulk store of this warp has completed
   }
 #undef IDEAS_HALO_DECODE
   ptx::tc_fence_before();
@@ -1065,6 +1108,24 @@ int halo_conv_launch_phases(const ConvGeom* gs, int nph, float* dst, const float
   }
   const uint32_t smem = p.w_stages * kHaloWBytes + p.x_stages * p.x_slot_bytes + kHaloStageBytes + 1024;
   p.epi = g_halo_epi.load();
+  if (p.epi >= 1 && g_halo_epi.load() != 3 && p.bw % 32 == 0) {
+    // tile rows made of 32-pixel segments (the tile search picks 32-wide tiles for 256, 64 and 32 pixel rows):
+    // TMA-store epilogue
+    p.epi = 2;
+    for (int f = 0; f < 4; ++f) {
+      const ConvGeom& q = gs[f < nph ? f : 0];
+      const uint64_t dims[4] = {(uint64_t)q.OC, (uint64_t)q.QW, (uint64_t)q.QH, (uint64_t)q.N};
+      const uint64_t strides[3] = {(uint64_t)q.o_s * q.OC * 4, (uint64_t)q.o_s * q.OW * q.OC * 4,
+                                   (uint64_t)q.OH * q.OW * q.OC * 4};
+      const uint32_t box[4] = {32u, 32u, 1u, 1u};
+      float* base = dst + ((int64_t)q.o_py * q.OW + q.o_px) * q.OC;
+      int rc = encode_map(&p.dmap[f], base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, true);
+      if (rc) return rc;
+    }
+  } else {
+    if (p.epi > 1) p.epi = 1;
+    memset(p.dmap, 0, sizeof(p.dmap));
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

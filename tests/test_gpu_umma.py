@@ -194,6 +194,9 @@ HALO_FWD_CASES = [
     (2, 64, 160, 9, 50, 3, 1),           # K = 160: second k-tile has 32 live rows
     (4, 384, 384, 14, 14, 3, 1),         # narrowest eligible rows (bwp = 16)
     (4, 768, 384, 17, 17, 2, 0),         # 2x2 valid conv (Dco head shape, larger image)
+    (1, 64, 64, 64, 64, 3, 1),           # 32-wide tiles: TMA-store epilogue, K = 64 clipped by the unit
+    (2, 32, 160, 32, 96, 3, 1),          # TMA-store epilogue, second k-tile has 32 live channels, 96-pixel rows
+    (1, 128, 128, 37, 128, 3, 1),        # TMA-store epilogue, ragged in y only
 ]
 
 
@@ -208,11 +211,15 @@ def test_halo_forward_matches_simt(case):
     b = torch.randn(K, device="cuda", generator=g)
     ref = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_SIMT, d, b, 1)
     n0 = L.launch_count()
-    with _halo(2):
+    with _halo(2), _opt(b"pmh", 0, 1):
         got = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA, d, b, 1)
         plain = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA)
+        n1 = L.launch_count()
+        with _opt(b"halo_epi", 3, 1):        # transposed 128-bit-store epilogue everywhere (no TMA stores)
+            transposed = conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_UMMA, d, b, 1)
     torch.cuda.synchronize()
-    assert L.launch_count() - n0 == 2
+    assert n1 - n0 == 2
+    assert torch.equal(got, transposed)      # the epilogue variants write the same bits
     assert not torch.isnan(got).any(), "unwritten outputs"
     assert rel(got, ref) <= 1e-3, rel(got, ref)
     assert rel(plain, conv_forward(x, wp, N, H, W, C, K, k, k, 1, pad, L.IMPL_SIMT)) <= 1e-3
@@ -240,6 +247,7 @@ def test_halo_dgrad_matches_simt(case):
 
 
 PHASED_DGRAD_CASES = [c for c in DGRAD_CASES if c[6] == 2 and c[5] == 3] + [
+    (2, 128, 256, 128, 128, 3, 2, 1),      # 64-pixel phase rows: 32-wide tiles, one strided TMA-store map per phase
     (2, 128, 256, 67, 65, 3, 2, 0),        # odd, non-square: the four phase grids differ in both directions
     (1, 64, 128, 130, 130, 3, 2, 1),       # padded stride-2 conv
     (2, 512, 512, 33, 33, 3, 2, 0),

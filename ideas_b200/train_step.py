@@ -43,6 +43,23 @@ def default_args(**overrides) -> argparse.Namespace:
     return argparse.Namespace(**d)
 
 
+_NVTX = __import__("os").environ.get("IDEAS_NVTX", "0") == "1"
+_nvtx_open = [False]
+
+
+def _nvtx_phase(name):
+    """IDEAS_NVTX=1: NVTX ranges around the phases of an eager training iteration (discriminators / lazy R1 /
+    encoder-generators-extractor), for timeline tools.  ``None`` closes the open range."""
+    if not _NVTX:
+        return
+    if _nvtx_open[0]:
+        torch.cuda.nvtx.range_pop()
+        _nvtx_open[0] = False
+    if name is not None:
+        torch.cuda.nvtx.range_push("ideas: " + name)
+        _nvtx_open[0] = True
+
+
 class FlatGradAllReduce:
     """Average the gradients of one optimiser's parameters across ranks with a single all-reduce on a flat fp32
     bucket (d-group 182 MB, g-group 257 MB, ex-group 1.5 MB).
@@ -405,6 +422,12 @@ class Trainer:
         return torch.cat([self.nets["Dreal"](x) for x in (x1, x2, x3)], 0)
 
     def _iteration(self, X, r1, late, draws, boxes, device_rng) -> Dict[str, torch.Tensor]:
+        try:
+            return self._iteration_body(X, r1, late, draws, boxes, device_rng)
+        finally:
+            _nvtx_phase(None)
+
+    def _iteration_body(self, X, r1, late, draws, boxes, device_rng) -> Dict[str, torch.Tensor]:
         a, t = self.args, self.nets
         H, W = X.shape[2], X.shape[3]
 
@@ -414,6 +437,7 @@ class Trainer:
             return draws[key] if (draws is not None and key in draws) else draw_crops(n, H, W)
 
         loss = {}
+        _nvtx_phase("discriminators")
         # ---------------- discriminators (train.py:48-102)
         for k in EMA_KEYS:
             requires_grad(t[k], False)
@@ -476,6 +500,7 @@ class Trainer:
         self.d_optim.step()
         # ---------------- lazy R1 (train.py:105-129)
         if r1:
+            _nvtx_phase("lazy R1")
             Xr = X.detach().requires_grad_(True)
             r1_real = d_r1_loss(t["Dreal"](Xr), Xr)
             rp = real_patch.detach().requires_grad_(True)
@@ -491,6 +516,7 @@ class Trainer:
             self.d_optim.step()
             loss.update(D_real_r1_loss=r1_real, D_texture_r1_loss=r1_tex, D_dist_r1_loss=r1_dist)
         # ---------------- encoder / generators / extractor (train.py:135-216)
+        _nvtx_phase("encoder / generators / extractor")
         for k in EMA_KEYS:
             requires_grad(t[k], True)
         for k in ("Dreal", "Dco", "Ddist"):

@@ -467,6 +467,55 @@ def test_styled_conv_path_length_second_order(cin, cout, res, up):
         CV.set_default_impl(old)
 
 
+@pytest.mark.parametrize("cin,cout,res,up", [(64, 64, 16, False), (64, 32, 16, True)])
+def test_styled_conv_path_length_second_order_tcgen05(cin, cout, res, up):
+    """The same double backward with every convolution of the first AND second order graph on the tcgen05 kernels
+    (tf32 operands): the penalty and its parameter / input gradients against the oracle, at the tf32 bounds of
+    tests/tolerances.py (gradients cross a leaky-ReLU mask twice)."""
+    from ideas_b200 import _lib as L
+    from ideas_b200.stylegan2 import model as M
+    from ideas_b200.stylegan2.op import conv as CV
+    from tolerances import record
+    old = CV.set_default_impl(L.IMPL_AUTO)
+    try:
+        torch.manual_seed(23)
+        m = M.StyledConv_without_noise(cin, cout, 3, 24, upsample=up)
+        m.activate.bias.data.normal_()
+        x = torch.randn(2, cin, res, res)
+        st = torch.rand(2, 24) * 2 - 1
+        sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "kernel" not in k)
+              for k, v in m.state_dict().items()}
+        names = ["conv.weight", "conv.modulation.weight", "conv.modulation.bias"]
+
+        def pl(fn_out, style, leaves):
+            noise = torch.randn(fn_out.shape, generator=torch.Generator().manual_seed(24)).to(fn_out.device)
+            (g,) = torch.autograd.grad((fn_out * noise).sum(), style, create_graph=True)
+            penalty = g.pow(2).sum(1).mean()
+            return penalty, torch.autograd.grad(penalty, leaves)
+
+        xr, sr = x.clone().requires_grad_(True), st.clone().requires_grad_(True)
+        want = O.styled_conv(xr, sr, sd["conv.weight"], sd["conv.modulation.weight"], sd["conv.modulation.bias"],
+                             sd["activate.bias"], upsample=up, blur_kernel=sd.get("conv.blur.kernel"))
+        p_want, g_want = pl(want, sr, [xr] + [sd[n] for n in names])
+        m = m.cuda()
+        xc, sc = x.cuda().requires_grad_(True), st.cuda().requires_grad_(True)
+        params = dict(m.named_parameters())
+        n0 = L.launch_count()
+        p_got, g_got = pl(m(xc, sc), sc, [xc] + [params[n] for n in names])
+        assert L.launch_count() > n0
+        errs = {"penalty": abs(float(p_got) - float(p_want)) / abs(float(p_want))}
+        for name, a, b in zip(["dx"] + names, g_got, g_want):
+            a, b = a.detach().cpu().double(), b.detach().double()
+            errs[name] = float((a - b).norm() / b.norm())
+        for name, e in errs.items():
+            record(f"pl_reg_tcgen05_{'up_' if up else ''}{name}", e)
+        # measured on B200: penalty 1.2e-3 (5.8e-3 up-sampling), gradients <= 1.6e-2 relative L2; bounds ~2x that
+        assert errs.pop("penalty") <= 1.2e-2, errs
+        assert max(errs.values()) <= 3e-2, errs
+    finally:
+        CV.set_default_impl(old)
+
+
 # ----------------------------------------------------------------------------------- A6 EqualLinear GEMM
 @pytest.mark.parametrize("shape", [(1, 1, 1), (3, 5, 7), (32, 512, 2048), (96, 1, 512), (128, 512, 8192), (33, 130, 70)])
 def test_matmul_nt_matches_fp64_any_strides(shape):

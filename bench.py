@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--prune-dead-backward", action="store_true",
                     help="NOT the default measurement: restrict the loop's second backward (train.py:214-216) to Ex's parameters")
+    ap.add_argument("--share-recon", action="store_true",
+                    help="NOT the default measurement: evaluate E(X) and G(E(X)) once per iteration instead of once per phase")
     return ap.parse_args()
 
 
@@ -456,7 +458,8 @@ def run_ours(args):
     targs = default_args(batch_size=B, image_size=S)
     tr = Trainer(targs, device=dev, seed=0, cuda_graphs=not args.no_graphs,   # same seed on every rank => identical replicas
                  multi_stream=False if args.single_stream else None,
-                 prune_dead_backward=args.prune_dead_backward, batch_generator=args.batch_g, split_dreal=args.split_dreal,
+                 prune_dead_backward=args.prune_dead_backward, share_recon=args.share_recon,
+                 batch_generator=args.batch_g, split_dreal=args.split_dreal,
                  concurrent_generator=not args.no_concurrent_g, early_generator=args.early_g)
     tr.broadcast_parameters(0)
     import random
@@ -535,6 +538,8 @@ def run_ours(args):
                    "r1_iterations_in_window": r1_in_window, "ms_per_step_plain": mean(ms_plain), "ms_per_step_r1": mean(ms_r1),
                    "ms_per_step_amortised_16": amort, "cuda_graphs": not args.no_graphs,
                    "second_backward": "Ex parameters only (pruned)" if args.prune_dead_backward else "full graph, as train.py:214-216",
+                   "recon_forward": ("E(X), G(E(X)) once per iteration (share_recon)" if args.share_recon
+                                     else "once per phase, as train.py:58,66,145,154"),
                    "l2": "activations of one step are tens of GB, far larger than the 126 MB L2; no explicit flush",
                    "est_tflops": FLOP_PER_IMAGE_STEP * value / 1e12 if S == 256 else None},
         "clocks": clocks, "gpu_launches": launches,

@@ -127,8 +127,15 @@ class Trainer:
     def __init__(self, args: argparse.Namespace, device="cuda", seed: Optional[int] = None, fused_adam: bool = True,
                  states: Optional[Dict[str, dict]] = None, cuda_graphs: bool = False, multi_stream: Optional[bool] = None,
                  prune_dead_backward: bool = False, batch_generator: bool = False, split_dreal: bool = False,
-                 concurrent_generator: bool = True, early_generator: bool = False):
+                 concurrent_generator: bool = True, early_generator: bool = False, share_recon: bool = False):
         self.args = args
+        # train.py evaluates S1, T1 = E(X) and hat_X1 = G(S1, T1) twice per iteration -- at :58,66 for the
+        # discriminators and again at :145,154 for the generators -- with the same weights (only d_optim steps in
+        # between) and the same input, i.e. with identical results.  With this flag they are evaluated ONCE, with
+        # their autograd graph, at the first place; the discriminator phase reads detached copies and the generator
+        # phase back-propagates through the graph kept from the first.  Same losses, same parameter trajectory, one
+        # E forward and one G forward less per iteration.  Off by default: bench.py measures the loop as written.
+        self.share_recon = bool(share_recon)
         self.batch_generator = bool(batch_generator)
         self.concurrent_generator = bool(concurrent_generator)
         self.early_generator = bool(early_generator)
@@ -359,14 +366,17 @@ class Trainer:
         with step_scope():                 # packed weights are built once per optimiser step, not once per call
             return self._iteration(X, r1, late, draws, boxes, device_rng)
 
-    def _generate3(self, S1, S2, T1, T2, streams=(2, 3)):
+    def _generate3(self, S1, S2, T1, T2, streams=(2, 3), x1=None, first=None):
         """hat_X1, hat_X2, hat_X3 = G(S1,T1), G(S2,T1), G(S2,T2) (train.py:66-70,154-158) and their concatenation
         (the argument of Dreal, train.py:73,161).  G is per-sample independent (no batch statistics), so the three
         calls may run as ONE call on the concatenated batch (``batch_generator=True``: same values and gradients, a
         third of the launches).  Measured on B200 at batch 32 it is 9 % SLOWER per step (334.7 vs 305.8 ms): at
         three times the working set the activations and weight slabs of consecutive kernels no longer meet in the
         126 MB L2, and the E(container) branch can no longer start under the third call.  Off by default."""
-        if not self.batch_generator:
+        # ``x1``: hat_X1 already evaluated (share_recon); ``first``: callable evaluating it (with its own autograd
+        # mode) in the slot of the first call
+        g1 = (lambda: x1) if x1 is not None else (first if first is not None else (lambda: self.nets["G"](S1, T1)))
+        if not self.batch_generator or x1 is not None or first is not None:
             if self.concurrent_generator and self.multi_stream:
                 # the three calls are independent chains of tensor-bound and HBM-bound kernels: on three streams the
                 # blur / activation kernels of one call run under the convolutions of another (autograd replays the
@@ -375,12 +385,12 @@ class Trainer:
                     x2 = self.nets["G"](S2, T1)
                 with self._fork(streams[1], S2, T2):
                     x3 = self.nets["G"](S2, T2)
-                x1 = self.nets["G"](S1, T1)
+                x1 = g1()
                 self._join(streams[0], x2)
                 self._join(streams[1], x3)
                 xs = (x1, x2, x3)
             else:
-                xs = self.nets["G"](S1, T1), self.nets["G"](S2, T1), self.nets["G"](S2, T2)
+                xs = g1(), self.nets["G"](S2, T1), self.nets["G"](S2, T2)
             return xs, (None if self.split_dreal else torch.cat(xs, 0))
         hat = self.nets["G"](torch.cat((S1, S2, S2), 0), torch.cat((T1, T1, T2), 0))
         return hat.chunk(3, 0), hat
@@ -456,10 +466,25 @@ class Trainer:
             # train.py:85-86 evaluates the fake patches first and reuses ref_input for the real ones; ref_input
             # does not depend on the first argument, so the order of the two calls is immaterial
             real_texture_pred, ref_input = t["Dco"](real_patch, ref_patch, ref_batch=a.ref_crop)
-        S1, T1 = t["E"](X)
+        shared = None
+        if self.share_recon:
+            # E(X) and G(E(X)) once for both phases: built here WITH their graph, read here through detached copies
+            requires_grad(t["E"], True)
+            S1g, T1g = t["E"](X)
+            requires_grad(t["E"], False)
+            S1, T1 = S1g.detach(), T1g.detach()
+            shared = dict(S1=S1g, T1=T1g)
+
+            def recon():
+                requires_grad(t["G"], True)
+                shared["hat_X1"] = t["G"](S1g, T1g)
+                requires_grad(t["G"], False)
+                return shared["hat_X1"].detach()
+        else:
+            S1, T1 = t["E"](X)
         S2 = t["Gstru"](Z)
         T2 = self._rand_like_T(T1, draws, "T2_d")
-        (hat_X1, hat_X2, hat_X3), hat_all = self._generate3(S1, S2, T1, T2)
+        (hat_X1, hat_X2, hat_X3), hat_all = self._generate3(S1, S2, T1, T2, first=recon if self.share_recon else None)
         fake_pred = self._dreal_fake(hat_X1, hat_X2, hat_X3, hat_all)
         fake_patch = patchify_image(hat_X2, a.n_crop, crops=fake_boxes)
         self._join(1, real_texture_pred, ref_input, real_patch, ref_patch)
@@ -478,14 +503,15 @@ class Trainer:
         def generator_forward(g_streams, drawn):
             """First part of the G / E / Ex phase (train.py:144-158): everything that does not read a discriminator."""
             Zg, fb, rb = drawn
-            S1g, T1g = t["E"](X)
+            S1g, T1g = (shared["S1"], shared["T1"]) if shared is not None else t["E"](X)
             S2g = t["Gstru"](Zg)
             T2g = self._rand_like_T(T1g, draws, "T2_g")
-            hats, hall = self._generate3(S1g, S2g, T1g, T2g, streams=g_streams)
+            hats, hall = self._generate3(S1g, S2g, T1g, T2g, streams=g_streams,
+                                         x1=shared["hat_X1"] if shared is not None else None)
             return dict(Z=Zg, fake_boxes=fb, ref_boxes=rb, S1=S1g, T1=T1g, S2=S2g, T2=T2g, hats=hats, hat_all=hall)
 
         early = None
-        if self.early_generator and self.multi_stream and not r1:
+        if self.early_generator and self.multi_stream and not r1 and not self.share_recon:
             # The generator-side forward of the next phase reads no discriminator, and E / G / Gstru do not change
             # in this one: start it on its own streams now, under the discriminators' backward pass and optimiser
             # step.  Same values, same order of random draws (the backward pass draws nothing).  Measured: no gain

@@ -335,6 +335,40 @@ def test_pruned_second_backward_same_parameters():
         assert float((d > 1e-5).float().mean()) < 0.02, (k, float(d.max()))
 
 
+def test_shared_reconstruction_forward_same_iteration():
+    """Trainer(share_recon=True) evaluates E(X) and G(E(X)) once per iteration (with their graph) instead of once per
+    phase (train.py:58,66 and :145,154 -- same weights, same input).  Starting from the same weights and draws, two
+    eager iterations (the second with lazy R1) must give the same losses and leave every network with the same
+    parameters (after the first) as the loop as written."""
+    from ideas_b200.train_step import Trainer, default_args
+    cfg = dict(channel=4, texture_channel=64, N=1, image_size=256, batch_size=2, d_reg_every=2)
+    X = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(3)) * 2 - 1).cuda()
+    runs, losses = [], []
+    draws = {it: _draws(2, 1, 16, 64, 256, 256, 8, 4) for it in (1, 2)}
+    for share in (False, True):
+        tr = Trainer(default_args(**cfg), device="cuda", seed=13, fused_adam=False, share_recon=share)
+        ls = []
+        for it in (1, 2):
+            out = tr.step(X, it, draws[it])
+            ls.append({k: float(v) for k, v in out.items()})
+            if it == 1:      # parameters are compared after ONE iteration: Adam turns the fp32-atomics noise of a second
+                #              one into O(lr) differences wherever a gradient is small
+                runs.append({k: torch.cat([p.detach().reshape(-1) for p in tr.nets[k].parameters()]) for k in tr.nets})
+        torch.cuda.synchronize()
+        losses.append(ls)
+    for it, (a, b) in enumerate(zip(*losses), 1):
+        assert a.keys() == b.keys()
+        # iteration 1 starts from identical weights: same values up to the order of fp32 atomics in the gradient sums;
+        # iteration 2 starts from weights that differ by the +-lr flips of ~0 gradients (see the graph test above)
+        tol = 2e-5 if it == 1 else 1e-2
+        for k in a:
+            assert abs(a[k] - b[k]) <= tol * max(1.0, abs(a[k])), (it, k, a[k], b[k])
+    for k in runs[0]:
+        d = (runs[0][k] - runs[1][k]).abs()
+        # the weight-gradient merge uses fp32 atomics: allow the +-lr flips of ~0 gradients (see the graph test above)
+        assert float((d > 1e-5).float().mean()) < 0.02, (k, float(d.max()))
+
+
 def test_sender_receiver_pipeline_matches_oracle():
     """ideas_b200.pipeline: message -> Gstru -> G -> image -> E -> Ex -> message on untrained 64x64 networks, against
     the oracle networks on the CPU run on the same secret tensor (train.py:254-286).  Untrained nets do not recover

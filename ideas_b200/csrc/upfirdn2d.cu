@@ -24,6 +24,8 @@ namespace ideas {
 static std::atomic<int> g_blur_variant{0};
 int blur_variant() { return g_blur_variant.load(); }
 void set_blur_variant(int v) { g_blur_variant.store(v); }
+static std::atomic<int> g_resample_variant{0};      // option "resample_variant": strip shapes of the up2 / down2 kernels
+void set_resample_variant(int v) { g_resample_variant.store(v); }
 
 struct UpfirdnParams {
   int major, in_h, in_w, minor, kh, kw;
@@ -686,6 +688,10 @@ extern "C" int ideas_upfirdn2d_res(float* out, const float* x, const float* kern
       };
       if (variant == 1) launch(std::integral_constant<int, 32>{}, std::integral_constant<int, 4>{});
       else if (variant == 2) launch(std::integral_constant<int, 64>{}, std::integral_constant<int, 4>{});
+      else if (variant == 4) launch(std::integral_constant<int, 32>{}, std::integral_constant<int, 1>{});
+      else if (variant == 5) launch(std::integral_constant<int, 16>{}, std::integral_constant<int, 1>{});
+      else if (variant == 6) launch(std::integral_constant<int, 16>{}, std::integral_constant<int, 2>{});
+      else if (variant == 7) launch(std::integral_constant<int, 64>{}, std::integral_constant<int, 1>{});
       else launch(std::integral_constant<int, 64>{}, std::integral_constant<int, 2>{});
       IDEAS_CHECK_LAUNCH("upfirdn2d(fast)");
       return IDEAS_OK;
@@ -701,17 +707,41 @@ extern "C" int ideas_upfirdn2d_res(float* out, const float* x, const float* kern
   const bool resample_ok = kernel_h <= 4 && kernel_w <= 4 && minor % 4 == 0 && aligned16(out) && aligned16(x) && !bias &&
                            major <= 65535;
   if (resample_ok && up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2) {
-    constexpr int ROWS = 16, XT = 2;
-    dim3 grid(ceil_div(ceil_div(p.out_w, XT) * (minor / 4), 128), ceil_div(p.out_h, ROWS), major);
-    blur4_down2_kernel<ROWS, XT><<<grid, 128, 0, st>>>(out, x, kernel, p);
+#define IDEAS_DOWN2(ROWS, XT)                                                                              \
+  {                                                                                                       \
+    dim3 grid(ceil_div(ceil_div(p.out_w, XT) * (minor / 4), 128), ceil_div(p.out_h, ROWS), major);        \
+    blur4_down2_kernel<ROWS, XT><<<grid, 128, 0, st>>>(out, x, kernel, p);                                \
+  }
+    switch (g_resample_variant.load()) {
+      case 1: IDEAS_DOWN2(32, 2) break;
+      case 2: IDEAS_DOWN2(8, 2) break;
+      case 3: IDEAS_DOWN2(16, 1) break;
+      case 4: IDEAS_DOWN2(32, 1) break;
+      case 5: IDEAS_DOWN2(16, 2) break;        // the default until scripts/bench_resample.py: 1.3-2.6x slower
+      case 6: IDEAS_DOWN2(4, 1) break;
+      default: IDEAS_DOWN2(8, 1) break;         // 8 output rows x 1 column per thread: most threads in flight
+    }
+#undef IDEAS_DOWN2
     IDEAS_CHECK_LAUNCH("upfirdn2d(down2)");
     return IDEAS_OK;
   }
   if (resample_ok && up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1) {
-    constexpr int ROWS = 32, XT = 2;
-    dim3 grid(ceil_div(ceil_div(p.out_w, 2 * XT) * (minor / 4), 128), ceil_div(p.out_h, ROWS), major);
-    if (pad_x0 & 1) blur4_up2_kernel<ROWS, XT, 1><<<grid, 128, 0, st>>>(out, x, kernel, p);
-    else blur4_up2_kernel<ROWS, XT, 0><<<grid, 128, 0, st>>>(out, x, kernel, p);
+#define IDEAS_UP2(ROWS, XT)                                                                                \
+  {                                                                                                       \
+    dim3 grid(ceil_div(ceil_div(p.out_w, 2 * XT) * (minor / 4), 128), ceil_div(p.out_h, ROWS), major);    \
+    if (pad_x0 & 1) blur4_up2_kernel<ROWS, XT, 1><<<grid, 128, 0, st>>>(out, x, kernel, p);               \
+    else blur4_up2_kernel<ROWS, XT, 0><<<grid, 128, 0, st>>>(out, x, kernel, p);                          \
+  }
+    switch (g_resample_variant.load()) {
+      case 1: IDEAS_UP2(16, 2) break;
+      case 2: IDEAS_UP2(64, 2) break;
+      case 3: IDEAS_UP2(32, 1) break;
+      case 4: IDEAS_UP2(32, 2) break;          // the default until scripts/bench_resample.py: 6-12 % slower
+      case 5: IDEAS_UP2(8, 1) break;
+      case 6: IDEAS_UP2(64, 1) break;
+      default: IDEAS_UP2(16, 1) break;          // 16 output rows x 2 columns per thread
+    }
+#undef IDEAS_UP2
     IDEAS_CHECK_LAUNCH("upfirdn2d(up2)");
     return IDEAS_OK;
   }

@@ -30,6 +30,7 @@ namespace ideas {
 
 void set_blur_variant(int v);   // upfirdn2d.cu
 void set_resample_variant(int v);
+void set_gemm_split(int v);      // linear.cu
 
 namespace {
 
@@ -2048,6 +2049,10 @@ extern "C" int ideas_set_option(const char* name, int value) {
   if (name && !strcmp(name, "dgrad_phases")) {
     if (value < 0 || value > 2) { ideas::set_error("ideas_set_option: dgrad_phases must be 0, 1 or 2"); return IDEAS_ERR_INVALID; }
     ideas::g_dgrad_phases.store(value);
+    return IDEAS_OK;
+  }
+  if (name && !strcmp(name, "gemm_split")) {
+    ideas::set_gemm_split(value);
     return IDEAS_OK;
   }
   if (name && !strcmp(name, "resample_variant")) {

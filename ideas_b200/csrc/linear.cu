@@ -13,7 +13,13 @@
 // gridDim.z and merged with fp32 atomics into the zero-initialised output.
 #include "common.cuh"
 
+#include <atomic>
+
 namespace ideas {
+
+static std::atomic<int> g_gemm_split{16};
+void set_gemm_split(int v) { g_gemm_split.store(v); }
+
 namespace {
 
 constexpr int kT = 32;       // C tile is kT x kT, reduction step kT
@@ -76,9 +82,19 @@ extern "C" int ideas_gemm_nt(float* c, const float* a, const float* b, int M, in
   if (M == 0 || N == 0) return IDEAS_OK;
   IDEAS_REQUIRE(c && (R == 0 || (a && b)), "gemm_nt: null pointer");
   const int tiles = ceil_div(M, kT) * ceil_div(N, kT);
+  // The maps on this path are skinny (M = batch): each CTA walks its share of the reduction as a serial chain of
+  // 32-wide steps, so the launch is latency bound unless there are several CTAs per SM.  Split the reduction until
+  // about `target` CTAs per SM exist (option "gemm_split": 16; 0 = the earlier rule, split only below one wave), every
+  // split keeping at least 4 steps.  The 16-linear modulation GEMM of a Generator call (32 x 5 000 x 2 048: 156 tiles
+  // of 64 steps) runs 16-way split: 149 -> 51 us (scripts/bench_gemm.py).
   int splits = 1;
-  if (c_is_zero && tiles < kNumSMs && R >= 8 * kT) {
-    splits = (2 * kNumSMs) / tiles;
+  const int target = g_gemm_split.load();
+  if (c_is_zero && R >= 8 * kT) {
+    if (target <= 0) {
+      if (tiles < kNumSMs) splits = (2 * kNumSMs) / tiles;
+    } else {
+      splits = ceil_div(target * kNumSMs, tiles);
+    }
     const int max_splits = R / (4 * kT);
     splits = splits > max_splits ? max_splits : splits;
     splits = splits < 1 ? 1 : splits;

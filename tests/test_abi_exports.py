@@ -63,6 +63,13 @@ def test_argument_validation_without_a_gpu():
     assert L.ideas_reflect_pad2d(p0, p0, 0, 4, 4, 4, 1, 0, p0) == 0
     # tuning knobs: known names accepted, unknown rejected with a message
     assert L.ideas_set_option(b"halo", 1) == 0 and L.ideas_set_option(b"wgrad_reuse", 1) == 0
+    # the knobs INTEGRATION.md lists, set to their defaults
+    for name, default in ((b"pmh", 1), (b"pmh_resident", 1), (b"tail_split", 1), (b"tma_tf32", 1), (b"blur_variant", 0),
+                          (b"pair", 1), (b"pair_epi", 1), (b"pair_stages", 0), (b"dgrad_phases", 1), (b"halo_epi", 1),
+                          (b"resample_variant", 0), (b"gemm_split", 16)):
+        assert L.ideas_set_option(name, default) == 0, name
+    assert L.ideas_set_option(b"dgrad_phases", 7) == -1          # out of range
+    assert L.ideas_set_option(b"dgrad_phases", 1) == 0
     assert L.ideas_set_option(b"no_such_option", 1) == -1
     assert b"unknown option" in L.ideas_last_error()
 
